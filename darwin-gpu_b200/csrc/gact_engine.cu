@@ -1,0 +1,708 @@
+// gact_engine.cu -- C ABI (include/gact_b200.h) of the B200 GACT tile engine.
+//
+// Replaces the reference's cuda_host.cu: GPU_init (:193-237), Align_Batch_GPU
+// (:23-190), GPU_close (:239-258).  Differences by design: sequences are
+// uploaded once and stay 2-bit packed in HBM (the reference re-copies every
+// tile's bases per batch, cuda_host.cu:85-163); descriptors/results travel
+// through pinned double-buffered slots; errors are returned, never exit().
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <new>
+
+#include "gact_common.cuh"
+#include "gact_kernels_i32.cuh"
+#include "gact_kernels_s16.cuh"
+
+using namespace gact;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct SeqSetHost {
+    uint32_t *d_packed = nullptr;
+    uint8_t *d_bytes = nullptr;
+    long long len = 0;
+    int bits = 0;
+    std::vector<long long> starts;
+};
+
+struct Slot {
+    gact_tile_desc *d_descs = nullptr, *h_descs = nullptr;
+    gact_tile_result *d_results = nullptr, *h_results = nullptr;
+    uint32_t *d_states = nullptr, *h_states = nullptr;
+    EffLen *d_eff = nullptr;
+    int *d_first = nullptr, *h_first = nullptr;
+    int *d_counters = nullptr;            // [0] first pass, [1] main pass
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    int n = 0, n_first = 0;
+    bool busy = false;
+    unsigned long long cells = 0;
+};
+
+}  // namespace
+
+struct gact_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    gact_params params{};
+    KParams kp{};
+    int max_tiles = 0;
+    int pitch_words = 0;
+    int num_sms = 0;
+    int variant_req = 0;      // 0 auto, 1 int32, 2 s16x2
+    int C = 0;                // columns per lane (int32 kernel)
+    bool dir_global = false;
+    size_t per_warp_bytes = 0;
+    int warps_per_cta = 0, ctas = 0;
+    size_t smem_main = 0;
+    uint8_t *d_gscratch = nullptr;
+    // s16x2 kernel launch plan
+    bool s16_ok = false;
+    int s16_C = 0;
+    size_t s16_per_warp_bytes = 0;
+    int s16_warps_per_cta = 0, s16_ctas = 0;
+    size_t s16_smem = 0;
+    SeqSetHost sets[GACT_MAX_SETS];
+    Slot slots[2];
+    int head = 0, tail = 0, inflight = 0;   // async ring
+    bool staged = false;
+    double last_kernel_ms = -1.0;
+    gact_stats stats{};
+    std::string err;
+};
+
+namespace {
+
+int fail(gact_engine *e, int code, const std::string &msg)
+{
+    if (e) e->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU(e, call)                                                                         \
+    do {                                                                                    \
+        cudaError_t _r = (call);                                                            \
+        if (_r != cudaSuccess)                                                              \
+            return fail((e), GACT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_r)); \
+    } while (0)
+
+// --------------------------------------------------------------------------
+// upload: raw bytes -> 2-bit words, and "is everything ACGT?" in one pass
+__global__ void pack2_kernel(const uint8_t *__restrict__ raw, long long len, uint32_t *__restrict__ packed,
+                             long long n_words, int *not_acgt)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    int bad = 0;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+        uint32_t v = 0;
+        const long long b0 = w * 16;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const long long idx = b0 + k;
+            if (idx < len) {
+                const int ch = raw[idx];
+                int code;
+                switch (ch) {
+                    case 'A': code = 0; break;
+                    case 'C': code = 1; break;
+                    case 'G': code = 2; break;
+                    case 'T': code = 3; break;
+                    default: code = 0; bad = 1; break;
+                }
+                v |= (uint32_t)code << (2 * k);
+            }
+        }
+        packed[w] = v;
+    }
+    if (bad) atomicOr(not_acgt, 1);
+}
+
+void free_set(SeqSetHost &s)
+{
+    if (s.d_packed) cudaFree(s.d_packed);
+    if (s.d_bytes) cudaFree(s.d_bytes);
+    s = SeqSetHost();
+}
+
+void free_slot(Slot &s)
+{
+    if (s.d_descs) cudaFree(s.d_descs);
+    if (s.d_results) cudaFree(s.d_results);
+    if (s.d_states) cudaFree(s.d_states);
+    if (s.d_eff) cudaFree(s.d_eff);
+    if (s.d_first) cudaFree(s.d_first);
+    if (s.d_counters) cudaFree(s.d_counters);
+    if (s.h_descs) cudaFreeHost(s.h_descs);
+    if (s.h_results) cudaFreeHost(s.h_results);
+    if (s.h_states) cudaFreeHost(s.h_states);
+    if (s.h_first) cudaFreeHost(s.h_first);
+    if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+    if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+    s = Slot();
+}
+
+// --------------------------------------------------------------------------
+// kernel dispatch tables
+typedef void (*main_fn)(const KParams, const gact_tile_desc *, int, const EffLen *, gact_tile_result *,
+                        uint32_t *, int, int *, uint8_t *, size_t);
+typedef void (*first_fn)(const KParams, const gact_tile_desc *, const int *, int, EffLen *, int *);
+
+main_fn pick_main_i32(int C, bool g)
+{
+    switch (C) {
+        case 8:  return g ? gact_tile_i32_kernel<8, true>  : gact_tile_i32_kernel<8, false>;
+        case 10: return g ? gact_tile_i32_kernel<10, true> : gact_tile_i32_kernel<10, false>;
+        case 16: return g ? gact_tile_i32_kernel<16, true> : gact_tile_i32_kernel<16, false>;
+        default: return g ? gact_tile_i32_kernel<32, true> : gact_tile_i32_kernel<32, false>;
+    }
+}
+first_fn pick_first_i32(int C)
+{
+    switch (C) {
+        case 8:  return gact_first_i32_kernel<8>;
+        case 10: return gact_first_i32_kernel<10>;
+        case 16: return gact_first_i32_kernel<16>;
+        default: return gact_first_i32_kernel<32>;
+    }
+}
+size_t dir_bytes_i32(int C, int rows, int lanes)
+{
+    switch (C) {
+        case 8:  return DirWin<8>::bytes(rows, lanes);
+        case 10: return DirWin<10>::bytes(rows, lanes);
+        case 16: return DirWin<16>::bytes(rows, lanes);
+        default: return DirWin<32>::bytes(rows, lanes);
+    }
+}
+
+const size_t SMEM_CTA_MAX = 227 * 1024;    // opt-in dynamic shared memory per CTA on sm_100
+const size_t SMEM_SM = 228 * 1024;         // per SM, 1 KB reserved per resident CTA
+
+int plan_launch(gact_engine *e)
+{
+    const int T = e->params.tile_size;
+    const int et = e->params.tile_size - e->params.tile_overlap;
+    e->C = (T <= 256) ? 8 : (T <= 320) ? 10 : (T <= 512) ? 16 : 32;
+    const int C = e->C;
+    const int TS = C * 32;
+    e->kp.win_rows = (et + 1 < T) ? et + 1 : T;
+    int wl = et / C + 2;
+    e->kp.win_lanes = wl > 32 ? 32 : wl;
+    const size_t dirb = dir_bytes_i32(C, e->kp.win_rows, e->kp.win_lanes);
+    const size_t smem_per_warp = TS + dirb;
+    // shared-memory window if at least 4 warps fit per SM, else L2-resident scratch
+    int fit = (int)((SMEM_SM - 2048) / smem_per_warp);
+    if (fit >= 4) {
+        e->dir_global = false;
+        e->per_warp_bytes = smem_per_warp;
+        int wpc = fit > 8 ? 8 : fit;
+        // prefer two CTAs per SM when that keeps more warps resident
+        int best_w = wpc, best_c = 1, best_total = wpc;
+        for (int w = 1; w <= 8; w++) {
+            const size_t cta = (size_t)w * smem_per_warp;
+            if (cta > SMEM_CTA_MAX) break;
+            int c = (int)(SMEM_SM / (cta + 1024));
+            if (c > 8) c = 8;
+            if (c * w > 32) c = 32 / w;
+            if (c * w > best_total || (c * w == best_total && w > best_w)) { best_total = c * w; best_w = w; best_c = c; }
+        }
+        e->warps_per_cta = best_w;
+        e->ctas = best_c * e->num_sms;
+        e->smem_main = (size_t)best_w * smem_per_warp;
+    } else {
+        e->dir_global = true;
+        e->per_warp_bytes = dirb;
+        e->warps_per_cta = 4;
+        const int ctas_per_sm = 4;
+        e->ctas = ctas_per_sm * e->num_sms;
+        e->smem_main = (size_t)e->warps_per_cta * TS;
+        const size_t total = (size_t)e->ctas * e->warps_per_cta * dirb;
+        if (cudaMalloc(&e->d_gscratch, total) != cudaSuccess)
+            return fail(e, GACT_ERR_NOMEM, "cudaMalloc(direction scratch) failed");
+    }
+    main_fn f = pick_main_i32(C, e->dir_global);
+    CU(e, cudaFuncSetAttribute((const void *)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_main));
+    first_fn ff = pick_first_i32(C);
+    CU(e, cudaFuncSetAttribute((const void *)ff, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * TS));
+    return s16_plan(e->params, e->num_sms, e->kp, &e->s16_ok, &e->s16_C, &e->s16_per_warp_bytes,
+                    &e->s16_warps_per_cta, &e->s16_ctas, &e->s16_smem) == 0
+               ? GACT_OK
+               : fail(e, GACT_ERR_CUDA, "s16 kernel attribute setup failed");
+}
+
+bool use_s16(const gact_engine *e)
+{
+    if (e->variant_req == 1) return false;
+    return e->s16_ok;
+}
+
+int launch_batch(gact_engine *e, Slot &s)
+{
+    cudaStream_t st = e->stream;
+    CU(e, cudaMemsetAsync(s.d_counters, 0, 2 * sizeof(int), st));
+    CU(e, cudaEventRecord(s.ev_k0, st));
+    const int TS = e->C * 32;
+    if (s.n_first > 0) {
+        first_fn ff = pick_first_i32(e->C);
+        int ctas = e->num_sms * 4;
+        int need = (s.n_first + 7) / 8;
+        if (need < ctas) ctas = need;
+        ff<<<ctas, 256, 8 * TS, st>>>(e->kp, s.d_descs, s.d_first, s.n_first, s.d_eff, s.d_counters + 0);
+        e->stats.kernel_launches++;
+    }
+    if (use_s16(e)) {
+        s16_launch(e->s16_C, e->kp, s.d_descs, s.n, s.d_eff, s.d_results, s.d_states, e->pitch_words,
+                   s.d_counters + 1, e->s16_per_warp_bytes, e->s16_warps_per_cta, e->s16_ctas, e->s16_smem, st);
+    } else {
+        main_fn f = pick_main_i32(e->C, e->dir_global);
+        int ctas = e->ctas;
+        int need = (s.n + e->warps_per_cta - 1) / e->warps_per_cta;
+        if (need < ctas) ctas = need;
+        f<<<ctas, e->warps_per_cta * 32, e->smem_main, st>>>(e->kp, s.d_descs, s.n, s.d_eff, s.d_results,
+                                                             s.d_states, e->pitch_words, s.d_counters + 1,
+                                                             e->d_gscratch, e->per_warp_bytes);
+    }
+    e->stats.kernel_launches++;
+    CU(e, cudaGetLastError());
+    CU(e, cudaEventRecord(s.ev_k1, st));
+    return GACT_OK;
+}
+
+int check_descs(gact_engine *e, int n, const gact_tile_desc *descs, Slot &s)
+{
+    const int T = e->params.tile_size;
+    int nf = 0;
+    unsigned long long cells = 0;
+    for (int t = 0; t < n; t++) {
+        const gact_tile_desc &d = descs[t];
+        if (d.ref_set >= GACT_MAX_SETS || d.query_set >= GACT_MAX_SETS || d.ref_len < 0 || d.query_len < 0 ||
+            d.ref_len > T || d.query_len > T || d.ref_off < 0 || d.query_off < 0 ||
+            d.ref_off + d.ref_len > e->sets[d.ref_set].len || d.query_off + d.query_len > e->sets[d.query_set].len)
+            return fail(e, GACT_ERR_ARG, "tile descriptor " + std::to_string(t) + " out of range");
+        if (d.first) s.h_first[nf++] = t;
+        cells += (unsigned long long)d.ref_len * (unsigned long long)d.query_len;
+    }
+    s.n_first = nf;
+    s.cells = cells;
+    return GACT_OK;
+}
+
+int enqueue(gact_engine *e, Slot &s, int n, const gact_tile_desc *descs)
+{
+    if (n < 0 || n > e->max_tiles || (n > 0 && !descs)) return fail(e, GACT_ERR_ARG, "bad tile count");
+    int rc = check_descs(e, n, descs, s);
+    if (rc) return rc;
+    s.n = n;
+    if (n == 0) return GACT_OK;
+    memcpy(s.h_descs, descs, (size_t)n * sizeof(gact_tile_desc));
+    CU(e, cudaMemcpyAsync(s.d_descs, s.h_descs, (size_t)n * sizeof(gact_tile_desc), cudaMemcpyHostToDevice, e->stream));
+    if (s.n_first)
+        CU(e, cudaMemcpyAsync(s.d_first, s.h_first, (size_t)s.n_first * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    e->stats.h2d_bytes += (double)n * sizeof(gact_tile_desc) + (double)s.n_first * sizeof(int);
+    return GACT_OK;
+}
+
+int download(gact_engine *e, Slot &s, bool want_states)
+{
+    if (s.n == 0) return GACT_OK;
+    CU(e, cudaMemcpyAsync(s.h_results, s.d_results, (size_t)s.n * sizeof(gact_tile_result), cudaMemcpyDeviceToHost, e->stream));
+    e->stats.d2h_bytes += (double)s.n * sizeof(gact_tile_result);
+    if (want_states) {
+        CU(e, cudaMemcpyAsync(s.h_states, s.d_states, (size_t)s.n * e->pitch_words * 4, cudaMemcpyDeviceToHost, e->stream));
+        e->stats.d2h_bytes += (double)s.n * e->pitch_words * 4;
+    }
+    return GACT_OK;
+}
+
+int finish(gact_engine *e, Slot &s, gact_tile_result *results, uint32_t *packed_states, bool states_copied)
+{
+    CU(e, cudaEventSynchronize(s.ev_done));
+    if (s.n > 0) {
+        float ms = 0.f;
+        CU(e, cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
+        e->last_kernel_ms = ms;
+        e->stats.kernel_ms += ms;
+        if (results) memcpy(results, s.h_results, (size_t)s.n * sizeof(gact_tile_result));
+        if (packed_states && states_copied) memcpy(packed_states, s.h_states, (size_t)s.n * e->pitch_words * 4);
+    }
+    e->stats.tiles += s.n;
+    e->stats.cells += s.cells;
+    e->stats.first_tiles += s.n_first;
+    e->stats.batches++;
+    return GACT_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+int gact_abi_version(void) { return GACT_B200_ABI_VERSION; }
+
+const char *gact_status_string(int status)
+{
+    switch (status) {
+        case GACT_OK: return "ok";
+        case GACT_ERR_ARG: return "bad argument";
+        case GACT_ERR_CUDA: return "CUDA error";
+        case GACT_ERR_NOMEM: return "out of memory";
+        case GACT_ERR_STATE: return "call sequence error";
+        case GACT_ERR_NODEVICE: return "no CUDA device";
+        default: return "unknown status";
+    }
+}
+
+int gact_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return n;
+}
+
+const char *gact_last_error(const gact_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int gact_engine_create(gact_engine **out, int device, const gact_params *p, int max_tiles, void *stream)
+{
+    if (!out || !p) return fail(nullptr, GACT_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (p->tile_size < 1 || p->tile_size > GACT_MAX_TILE_SIZE || p->tile_overlap < 0 ||
+        p->tile_overlap >= p->tile_size)
+        return fail(nullptr, GACT_ERR_ARG, "tile_size/tile_overlap out of range");
+    if (p->gap_open > 0 || p->gap_extend > 0)
+        return fail(nullptr, GACT_ERR_ARG, "gap_open and gap_extend must be <= 0");
+    if (abs(p->match) > 1024 || abs(p->mismatch) > 1024 || p->gap_open < -1024 || p->gap_extend < -1024)
+        return fail(nullptr, GACT_ERR_ARG, "scores out of range (|score| <= 1024)");
+    if (max_tiles < 1) return fail(nullptr, GACT_ERR_ARG, "max_tiles_per_batch must be >= 1");
+    int ndev = gact_device_count();
+    if (ndev <= 0) return fail(nullptr, GACT_ERR_NODEVICE, "no CUDA device available");
+    if (device < 0 || device >= ndev) return fail(nullptr, GACT_ERR_ARG, "device index out of range");
+
+    gact_engine *e = new (std::nothrow) gact_engine();
+    if (!e) return fail(nullptr, GACT_ERR_NOMEM, "host allocation failed");
+    e->device = device;
+    e->params = *p;
+    e->max_tiles = max_tiles;
+    int rc = GACT_OK;
+#define CK(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t _r = (call);                                                                 \
+        if (_r != cudaSuccess) {                                                                 \
+            rc = fail(nullptr, GACT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_r)); \
+            goto bad;                                                                            \
+        }                                                                                        \
+    } while (0)
+    {
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) {
+            rc = fail(nullptr, GACT_ERR_NODEVICE, "device is not sm_100 class (this library is built for sm_100a only)");
+            goto bad;
+        }
+        e->num_sms = prop.multiProcessorCount;
+        if (stream) { e->stream = (cudaStream_t)stream; e->owns_stream = false; }
+        else { CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->owns_stream = true; }
+
+        const int et = p->tile_size - p->tile_overlap;
+        e->pitch_words = (2 * et + 15) / 16 + 1;
+        e->kp.match = p->match; e->kp.mismatch = p->mismatch;
+        e->kp.gap_open = p->gap_open; e->kp.gap_extend = p->gap_extend;
+        e->kp.et = et; e->kp.tile_size = p->tile_size;
+        for (int i = 0; i < GACT_MAX_SETS; i++) e->kp.sets[i] = SeqSetDev{nullptr, nullptr, 0};
+
+        rc = plan_launch(e);
+        if (rc) { g_create_error = e->err; goto bad; }
+
+        for (int k = 0; k < 2; k++) {
+            Slot &s = e->slots[k];
+            const size_t n = (size_t)max_tiles;
+            CK(cudaMalloc(&s.d_descs, n * sizeof(gact_tile_desc)));
+            CK(cudaMalloc(&s.d_results, n * sizeof(gact_tile_result)));
+            CK(cudaMalloc(&s.d_states, n * e->pitch_words * 4));
+            CK(cudaMalloc(&s.d_eff, n * sizeof(EffLen)));
+            CK(cudaMalloc(&s.d_first, n * sizeof(int)));
+            CK(cudaMalloc(&s.d_counters, 2 * sizeof(int)));
+            CK(cudaMallocHost(&s.h_descs, n * sizeof(gact_tile_desc)));
+            CK(cudaMallocHost(&s.h_results, n * sizeof(gact_tile_result)));
+            CK(cudaMallocHost(&s.h_states, n * e->pitch_words * 4));
+            CK(cudaMallocHost(&s.h_first, n * sizeof(int)));
+            CK(cudaEventCreate(&s.ev_k0));
+            CK(cudaEventCreate(&s.ev_k1));
+            CK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+        }
+    }
+#undef CK
+    *out = e;
+    return GACT_OK;
+bad:
+    gact_engine_destroy(e);
+    return rc;
+}
+
+void gact_engine_destroy(gact_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (int i = 0; i < GACT_MAX_SETS; i++) free_set(e->sets[i]);
+    for (int k = 0; k < 2; k++) free_slot(e->slots[k]);
+    if (e->d_gscratch) cudaFree(e->d_gscratch);
+    if (e->owns_stream && e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int gact_engine_upload(gact_engine *e, int set, int64_t n_seqs, const char *const *seqs, const int64_t *lens)
+{
+    if (!e) return GACT_ERR_ARG;
+    if (set < 0 || set >= GACT_MAX_SETS || n_seqs < 0 || (n_seqs > 0 && (!seqs || !lens)))
+        return fail(e, GACT_ERR_ARG, "bad upload arguments");
+    if (e->inflight || e->staged) return fail(e, GACT_ERR_STATE, "upload while batches are outstanding");
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaStreamSynchronize(e->stream));
+    SeqSetHost &s = e->sets[set];
+    free_set(s);
+    e->kp.sets[set] = SeqSetDev{nullptr, nullptr, 0};
+    long long total = 0;
+    s.starts.resize((size_t)n_seqs + 1);
+    for (int64_t i = 0; i < n_seqs; i++) {
+        if (lens[i] < 0 || (lens[i] > 0 && !seqs[i])) return fail(e, GACT_ERR_ARG, "bad sequence in upload");
+        s.starts[(size_t)i] = total;
+        total += lens[i];
+    }
+    s.starts[(size_t)n_seqs] = total;
+    s.len = total;
+    if (total == 0) { s.bits = 0; return GACT_OK; }
+
+    // stage through pinned memory in chunks, concatenating on the device
+    uint8_t *d_raw = nullptr;
+    const long long padded = (total + 63) & ~63LL;
+    if (cudaMalloc(&d_raw, (size_t)padded) != cudaSuccess) { cudaGetLastError(); return fail(e, GACT_ERR_NOMEM, "cudaMalloc(raw bases) failed"); }
+    const size_t CH = 32u << 20;
+    uint8_t *h_stage = nullptr;
+    if (cudaMallocHost(&h_stage, CH) != cudaSuccess) { cudaGetLastError(); cudaFree(d_raw); return fail(e, GACT_ERR_NOMEM, "cudaMallocHost(stage) failed"); }
+    long long done = 0;        // bases already sent
+    size_t fill = 0;
+    int rc = GACT_OK;
+    auto flush = [&]() -> int {
+        if (!fill) return GACT_OK;
+        cudaError_t r = cudaMemcpyAsync(d_raw + done, h_stage, fill, cudaMemcpyHostToDevice, e->stream);
+        if (r == cudaSuccess) r = cudaStreamSynchronize(e->stream);
+        if (r != cudaSuccess) return fail(e, GACT_ERR_CUDA, std::string("upload copy: ") + cudaGetErrorString(r));
+        done += (long long)fill;
+        fill = 0;
+        return GACT_OK;
+    };
+    for (int64_t i = 0; i < n_seqs && rc == GACT_OK; i++) {
+        long long off = 0;
+        while (off < lens[i]) {
+            size_t take = (size_t)std::min<long long>(lens[i] - off, (long long)(CH - fill));
+            memcpy(h_stage + fill, seqs[i] + off, take);
+            fill += take; off += (long long)take;
+            if (fill == CH && (rc = flush()) != GACT_OK) break;
+        }
+    }
+    if (rc == GACT_OK) rc = flush();
+    cudaFreeHost(h_stage);
+    if (rc != GACT_OK) { cudaFree(d_raw); return rc; }
+    e->stats.h2d_bytes += (double)total;
+
+    const long long n_words = (total + 15) / 16 + 1;     // +1 pad word: tiles may peek past the end
+    uint32_t *d_packed = nullptr;
+    int *d_flag = nullptr;
+    if (cudaMalloc(&d_packed, (size_t)n_words * 4) != cudaSuccess || cudaMalloc(&d_flag, sizeof(int)) != cudaSuccess) {
+        cudaGetLastError(); cudaFree(d_raw); if (d_packed) cudaFree(d_packed);
+        return fail(e, GACT_ERR_NOMEM, "cudaMalloc(packed bases) failed");
+    }
+    int h_flag = 0;
+    cudaMemsetAsync(d_flag, 0, sizeof(int), e->stream);
+    cudaMemsetAsync(d_packed, 0, (size_t)n_words * 4, e->stream);
+    int blocks = (int)std::min<long long>((n_words + 255) / 256, (long long)e->num_sms * 8);
+    pack2_kernel<<<blocks, 256, 0, e->stream>>>(d_raw, total, d_packed, n_words - 1, d_flag);
+    cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+    cudaError_t r = cudaStreamSynchronize(e->stream);
+    cudaFree(d_flag);
+    if (r != cudaSuccess) { cudaFree(d_raw); cudaFree(d_packed); return fail(e, GACT_ERR_CUDA, std::string("pack kernel: ") + cudaGetErrorString(r)); }
+    if (h_flag) { cudaFree(d_packed); s.d_bytes = d_raw; s.bits = 8; }
+    else        { cudaFree(d_raw); s.d_packed = d_packed; s.bits = 2; }
+    e->kp.sets[set] = SeqSetDev{s.d_packed, s.d_bytes, s.len};
+    return GACT_OK;
+}
+
+int64_t gact_engine_seq_start(const gact_engine *e, int set, int64_t i)
+{
+    if (!e || set < 0 || set >= GACT_MAX_SETS) return -1;
+    const SeqSetHost &s = e->sets[set];
+    if (i < 0 || (size_t)i >= s.starts.size()) return -1;
+    return s.starts[(size_t)i];
+}
+int64_t gact_engine_set_length(const gact_engine *e, int set)
+{
+    if (!e || set < 0 || set >= GACT_MAX_SETS) return -1;
+    return e->sets[set].len;
+}
+int gact_engine_set_bits(const gact_engine *e, int set)
+{
+    if (!e || set < 0 || set >= GACT_MAX_SETS) return -1;
+    return e->sets[set].bits;
+}
+int gact_engine_states_pitch_words(const gact_engine *e) { return e ? e->pitch_words : -1; }
+int gact_engine_max_tiles(const gact_engine *e) { return e ? e->max_tiles : -1; }
+
+int gact_engine_submit(gact_engine *e, int n, const gact_tile_desc *descs)
+{
+    if (!e) return GACT_ERR_ARG;
+    if (e->staged) return fail(e, GACT_ERR_STATE, "submit while a staged batch is pending");
+    if (e->inflight >= 2) return fail(e, GACT_ERR_STATE, "two batches already in flight");
+    CU(e, cudaSetDevice(e->device));
+    Slot &s = e->slots[e->head];
+    int rc = enqueue(e, s, n, descs);
+    if (rc) return rc;
+    if (n > 0) {
+        rc = launch_batch(e, s);
+        if (rc) return rc;
+        rc = download(e, s, true);
+        if (rc) return rc;
+    }
+    CU(e, cudaEventRecord(s.ev_done, e->stream));
+    s.busy = true;
+    e->head ^= 1;
+    e->inflight++;
+    return GACT_OK;
+}
+
+int gact_engine_wait(gact_engine *e, gact_tile_result *results, uint32_t *packed_states)
+{
+    if (!e) return GACT_ERR_ARG;
+    if (e->inflight == 0) return fail(e, GACT_ERR_STATE, "wait without submit");
+    CU(e, cudaSetDevice(e->device));
+    Slot &s = e->slots[e->tail];
+    int rc = finish(e, s, results, packed_states, true);
+    s.busy = false;
+    e->tail ^= 1;
+    e->inflight--;
+    return rc;
+}
+
+int gact_engine_align_tiles(gact_engine *e, int n, const gact_tile_desc *descs,
+                            gact_tile_result *results, uint32_t *packed_states)
+{
+    if (!e) return GACT_ERR_ARG;
+    if (e->inflight) return fail(e, GACT_ERR_STATE, "align_tiles while async batches are in flight");
+    if (e->staged) return fail(e, GACT_ERR_STATE, "align_tiles while a staged batch is pending");
+    CU(e, cudaSetDevice(e->device));
+    Slot &s = e->slots[0];
+    int rc = enqueue(e, s, n, descs);
+    if (rc) return rc;
+    if (n > 0) {
+        rc = launch_batch(e, s);
+        if (rc) return rc;
+        rc = download(e, s, packed_states != nullptr);
+        if (rc) return rc;
+    }
+    CU(e, cudaEventRecord(s.ev_done, e->stream));
+    return finish(e, s, results, packed_states, packed_states != nullptr);
+}
+
+int gact_engine_stage(gact_engine *e, int n, const gact_tile_desc *descs)
+{
+    if (!e) return GACT_ERR_ARG;
+    if (e->inflight) return fail(e, GACT_ERR_STATE, "stage while async batches are in flight");
+    CU(e, cudaSetDevice(e->device));
+    Slot &s = e->slots[0];
+    int rc = enqueue(e, s, n, descs);
+    if (rc) return rc;
+    CU(e, cudaStreamSynchronize(e->stream));
+    e->staged = true;
+    return GACT_OK;
+}
+
+int gact_engine_run_staged(gact_engine *e)
+{
+    if (!e) return GACT_ERR_ARG;
+    if (!e->staged) return fail(e, GACT_ERR_STATE, "run_staged without stage");
+    CU(e, cudaSetDevice(e->device));
+    Slot &s = e->slots[0];
+    if (s.n == 0) return GACT_OK;
+    int rc = launch_batch(e, s);
+    if (rc) return rc;
+    e->stats.tiles += s.n;
+    e->stats.cells += s.cells;
+    e->stats.first_tiles += s.n_first;
+    e->stats.batches++;
+    return GACT_OK;
+}
+
+int gact_engine_sync(gact_engine *e)
+{
+    if (!e) return GACT_ERR_ARG;
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return GACT_OK;
+}
+
+double gact_engine_last_kernel_ms(gact_engine *e)
+{
+    if (!e) return -1.0;
+    if (e->staged) {
+        Slot &s = e->slots[0];
+        if (s.n == 0) return -1.0;
+        if (cudaSetDevice(e->device) != cudaSuccess) return -1.0;
+        if (cudaEventSynchronize(s.ev_k1) != cudaSuccess) return -1.0;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+        return ms;
+    }
+    return e->last_kernel_ms;
+}
+
+int gact_engine_fetch_staged(gact_engine *e, gact_tile_result *results, uint32_t *packed_states)
+{
+    if (!e) return GACT_ERR_ARG;
+    if (!e->staged) return fail(e, GACT_ERR_STATE, "fetch_staged without stage");
+    CU(e, cudaSetDevice(e->device));
+    Slot &s = e->slots[0];
+    int rc = download(e, s, packed_states != nullptr);
+    if (rc) return rc;
+    CU(e, cudaStreamSynchronize(e->stream));
+    if (s.n > 0) {
+        if (results) memcpy(results, s.h_results, (size_t)s.n * sizeof(gact_tile_result));
+        if (packed_states) memcpy(packed_states, s.h_states, (size_t)s.n * e->pitch_words * 4);
+    }
+    e->staged = false;
+    return GACT_OK;
+}
+
+int gact_engine_stats(const gact_engine *e, gact_stats *out)
+{
+    if (!e || !out) return GACT_ERR_ARG;
+    *out = e->stats;
+    return GACT_OK;
+}
+int gact_engine_reset_stats(gact_engine *e)
+{
+    if (!e) return GACT_ERR_ARG;
+    e->stats = gact_stats{};
+    return GACT_OK;
+}
+
+int gact_engine_set_kernel(gact_engine *e, int variant)
+{
+    if (!e) return GACT_ERR_ARG;
+    if (variant < 0 || variant > 2) return fail(e, GACT_ERR_ARG, "unknown kernel variant");
+    if (variant == 2 && !e->s16_ok) return fail(e, GACT_ERR_ARG, "s16x2 kernel cannot run these parameters");
+    e->variant_req = variant;
+    return GACT_OK;
+}
+int gact_engine_get_kernel(const gact_engine *e)
+{
+    if (!e) return GACT_ERR_ARG;
+    return use_s16(e) ? 2 : 1;
+}
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+"""Regenerates the golden fixtures from the UNMODIFIED reference built in place
+(oracle/Makefile -> oracle/_ref/libalign_ref.so and oracle/_ref/darwin_ref).
+Runs only in the build container (needs /root/reference); the fixtures it writes are committed.
+
+  align_random.npz  -- random tiles through the reference's AlignWithBT (align.cpp:60-233)
+  e2e_small/        -- a small read set + the reference CPU build's sorted|uniq output
+                       (README:32 / x_scalingrun.sh:27-33 recipe), per tile_size config
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "darwin-gpu_b200")]
+import oracle as O      # noqa: E402
+import synth            # noqa: E402
+
+
+def make_align_random():
+    rng = np.random.default_rng(20261018)
+    schemes = [(1, -1, -1, -1), (2, -3, -5, -2), (1, -1, -2, -1), (5, -4, -10, -1), (1, -3, 0, 0), (3, -1, -1, -4)]
+    refs, queries, meta, queues = [], [], [], []
+    for it in range(360):
+        T = int(rng.choice([320, 320, 320, 64, 17, 1, 5, 200, 256]))
+        sc = schemes[it % len(schemes)]
+        full = it % 3 == 0
+        rl = T if full else int(rng.integers(1, T + 1))
+        ql = T if full else int(rng.integers(1, T + 1))
+        g = synth.random_genome(rl, rng)
+        q, _ = synth.error_channel(g, rng)
+        q = np.concatenate([q, synth.random_genome(T, rng)])[:ql]
+        if it % 11 == 0:
+            q = np.frombuffer(b"ACGTNacgt", dtype=np.uint8)[rng.integers(0, 9, size=ql)]
+        if it % 13 == 0:
+            q = synth.random_genome(ql, rng)          # unrelated: low scores, ZERO states
+        rev, first = it % 2, (it // 2) % 2
+        et = int(rng.choice([200, 200, 4, 1, 50, 400]))
+        ref_q = O.ref_align_tile(g.tobytes(), q.tobytes(), sc, rev, first, et)
+        refs.append(g.tobytes()); queries.append(q.tobytes())
+        meta.append(list(sc) + [rev, first, et])
+        queues.append(np.asarray(ref_q, dtype=np.int32))
+    np.savez_compressed(os.path.join(HERE, "align_random.npz"),
+                        refs=np.array(refs, dtype=object), queries=np.array(queries, dtype=object),
+                        meta=np.asarray(meta, dtype=np.int32), queues=np.array(queues, dtype=object),
+                        allow_pickle=True)
+    print("align_random.npz:", len(refs), "tiles")
+
+
+PARAMS = """[GACT_scoring]
+match = {ma}
+mismatch = {mi}
+gap_open = {go}
+gap_extend = {ge}
+[DSOFT_params]
+seed_size = 14
+bin_size = 64
+window_size = 4
+threshold = 21
+num_seeds = 800
+seed_occurence_multiple = 32
+max_candidates = 1000000
+num_nz_bins = 2500000
+[GACT_first_tile]
+first_tile_size = 128
+first_tile_score_threshold = 35
+[GACT_extend]
+tile_size = {ts}
+tile_overlap = {to}
+"""
+
+
+def run_ref(workdir, ref_fa, reads_fa, threads, cfg):
+    os.makedirs(workdir, exist_ok=True)
+    with open(os.path.join(workdir, "params.cfg"), "w") as f:
+        f.write(PARAMS.format(**cfg))
+    for fn in os.listdir(workdir):
+        if fn.startswith("darwin.") and fn.endswith(".out"):
+            os.remove(os.path.join(workdir, fn))
+    subprocess.run([O.REF_DARWIN, ref_fa, reads_fa, str(threads)], cwd=workdir, check=True,
+                   stdout=subprocess.DEVNULL)
+    lines = []
+    for fn in sorted(os.listdir(workdir)):
+        if fn.startswith("darwin.") and fn.endswith(".out"):
+            lines += open(os.path.join(workdir, fn)).read().splitlines()
+    return sorted(set(lines))
+
+
+def make_e2e_small():
+    out = os.path.join(HERE, "e2e_small")
+    os.makedirs(out, exist_ok=True)
+    rng = np.random.default_rng(7)
+    genome = [synth.random_genome(60000, rng), synth.random_genome(45000, rng)]
+    synth.write_fasta(os.path.join(out, "ref.fasta"), ["chrA extra words", "chrB"], genome)
+    names, reads = synth.sample_reads(genome, 160000, rng, mean=3000, sd=1500, lo=300, hi=9000)
+    # a lower-case / N-containing read exercises the raw-byte comparison (align.cpp:134)
+    r = reads[3].copy(); r[100:140] = np.frombuffer(b"N", dtype=np.uint8)[0]; r[500:520] += 32; reads[3] = r
+    synth.write_fasta(os.path.join(out, "reads.fasta"), names, reads)
+    tmp = "/tmp/golden_e2e"
+    cfgs = {"t320": dict(ma=1, mi=-1, go=-1, ge=-1, ts=320, to=120),
+            "t256": dict(ma=1, mi=-1, go=-1, ge=-1, ts=256, to=96),
+            "t512_s2": dict(ma=2, mi=-3, go=-5, ge=-2, ts=512, to=192)}
+    for tag, cfg in cfgs.items():
+        lines = run_ref(tmp, os.path.join(out, "ref.fasta"), os.path.join(out, "reads.fasta"), 3, cfg)
+        open(os.path.join(out, f"expected_{tag}.txt"), "w").write("\n".join(lines) + "\n")
+        print(tag, "reads-vs-ref lines:", len(lines))
+    # de-novo self alignment (same file name on both sides -> same_file suppression, gact.cpp:213)
+    lines = run_ref(tmp, os.path.join(out, "reads.fasta"), os.path.join(out, "reads.fasta"), 3, cfgs["t320"])
+    open(os.path.join(out, "expected_self_t320.txt"), "w").write("\n".join(lines) + "\n")
+    print("self lines:", len(lines))
+
+
+if __name__ == "__main__":
+    O.build(ref=True)
+    make_align_random()
+    make_e2e_small()
