@@ -61,12 +61,7 @@ struct gact_engine {
     int warps_per_cta = 0, ctas = 0;
     size_t smem_main = 0;
     uint8_t *d_gscratch = nullptr;
-    // s16x2 kernel launch plan
-    bool s16_ok = false;
-    int s16_C = 0;
-    size_t s16_per_warp_bytes = 0;
-    int s16_warps_per_cta = 0, s16_ctas = 0;
-    size_t s16_smem = 0;
+    S16Plan s16;              // packed s16x2 kernel launch plan (s16.ok: usable for these params)
     SeqSetHost sets[GACT_MAX_SETS];
     Slot slots[2];
     int head = 0, tail = 0, inflight = 0;   // async ring
@@ -230,8 +225,7 @@ int plan_launch(gact_engine *e)
     CU(e, cudaFuncSetAttribute((const void *)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_main));
     first_fn ff = pick_first_i32(C);
     CU(e, cudaFuncSetAttribute((const void *)ff, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * TS));
-    return s16_plan(e->params, e->num_sms, e->kp, &e->s16_ok, &e->s16_C, &e->s16_per_warp_bytes,
-                    &e->s16_warps_per_cta, &e->s16_ctas, &e->s16_smem) == 0
+    return s16_make_plan(e->params, e->num_sms, &e->s16) == 0
                ? GACT_OK
                : fail(e, GACT_ERR_CUDA, "s16 kernel attribute setup failed");
 }
@@ -239,7 +233,7 @@ int plan_launch(gact_engine *e)
 bool use_s16(const gact_engine *e)
 {
     if (e->variant_req == 1) return false;
-    return e->s16_ok;
+    return e->s16.ok;
 }
 
 int launch_batch(gact_engine *e, Slot &s)
@@ -257,8 +251,8 @@ int launch_batch(gact_engine *e, Slot &s)
         e->stats.kernel_launches++;
     }
     if (use_s16(e)) {
-        s16_launch(e->s16_C, e->kp, s.d_descs, s.n, s.d_eff, s.d_results, s.d_states, e->pitch_words,
-                   s.d_counters + 1, e->s16_per_warp_bytes, e->s16_warps_per_cta, e->s16_ctas, e->s16_smem, st);
+        s16_launch(e->s16, e->kp, s.d_descs, s.n, s.d_eff, s.d_results, s.d_states, e->pitch_words,
+                   s.d_counters + 1, st);
     } else {
         main_fn f = pick_main_i32(e->C, e->dir_global);
         int ctas = e->ctas;
@@ -695,7 +689,7 @@ int gact_engine_set_kernel(gact_engine *e, int variant)
 {
     if (!e) return GACT_ERR_ARG;
     if (variant < 0 || variant > 2) return fail(e, GACT_ERR_ARG, "unknown kernel variant");
-    if (variant == 2 && !e->s16_ok) return fail(e, GACT_ERR_ARG, "s16x2 kernel cannot run these parameters");
+    if (variant == 2 && !e->s16.ok) return fail(e, GACT_ERR_ARG, "s16x2 kernel cannot run these parameters");
     e->variant_req = variant;
     return GACT_OK;
 }

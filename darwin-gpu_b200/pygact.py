@@ -219,7 +219,7 @@ class GactEngine:
         self._last_n.append(len(descs))
 
     def wait(self):
-        n = self._last_n.pop(0)
+        n = self._last_n.pop(0) if getattr(self, "_last_n", None) else 0
         res, st = self._bufs(n)
         self._ck(self.L.gact_engine_wait(self.h, res.ctypes.data, st.ctypes.data), "gact_engine_wait")
         return res, st

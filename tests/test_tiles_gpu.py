@@ -156,8 +156,10 @@ def test_async_submit_wait_matches_sync(pygact):
         sync = [eng.align_tiles(d[k:k + 1000]) for k in range(0, 3000, 1000)]
         eng.submit(d[0:1000]); eng.submit(d[1000:2000])
         a = eng.wait(); eng.submit(d[2000:3000]); b = eng.wait(); c = eng.wait()
+        from helpers import unpack_all
         for (r1, s1), (r2, s2) in zip(sync, [a, b, c]):
-            assert (r1 == r2).all() and (s1 == s2).all()
+            assert (r1 == r2).all()
+            assert (unpack_all(s1, r1["n_states"], 400) == unpack_all(s2, r2["n_states"], 400)).all()
         with pytest.raises(G.GactError):
             eng.wait()
         eng.stage(d[:512]); eng.run_staged(); eng.run_staged()
@@ -193,13 +195,14 @@ def test_large_batch_properties(pygact, oracle):
         d = engine_descs(G, mb)
         res, st = eng.align_tiles(d)
         res2, st2 = eng.align_tiles(d)
-    assert (res == res2).all() and (st == st2).all()                      # deterministic
+    from helpers import unpack_all
+    assert (res == res2).all()                                            # deterministic
+    assert (unpack_all(st, res["n_states"], 400) == unpack_all(st2, res2["n_states"], 400)).all()
     assert (res["n_states"] <= 2 * 200 - 1).all()
     assert (np.maximum(res["i_steps"], res["j_steps"]) <= 200).all()
     assert (res["i_steps"] <= mb["ref_len"]).all() and (res["j_steps"] <= mb["query_len"]).all()
     nf = mb["first"] == 0
     assert (res["max_i"][nf] == mb["ref_len"][nf]).all() and (res["max_j"][nf] == mb["query_len"][nf]).all()
-    from helpers import unpack_all
     u = unpack_all(st, res["n_states"], 400)
     assert ((u == 3) | (u == 2)).sum(axis=1).tolist() == res["i_steps"].tolist()
     assert ((u == 3) | (u == 1)).sum(axis=1).tolist() == res["j_steps"].tolist()
