@@ -122,7 +122,7 @@ def make_batch(n_tiles, seed):
     return synth.tile_microbatch(n_tiles, tile_size=TILE, seed=seed)
 
 
-def cpu_arm(args, mb, seconds):
+def cpu_arm(args, mb, seconds, gpu_scores=None):
     """Reference CPU AlignWithBT (oracle/_ref) or the oracle port, all host threads, bounded sample."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
@@ -133,13 +133,17 @@ def cpu_arm(args, mb, seconds):
         od[k] = mb[k]
     use_ref = O.ref_available()
 
+    scores = np.zeros(n, dtype=np.int32)
+
     def run(k):
         t0 = time.perf_counter()
         if use_ref:
             cells = O.ref_lib().ref_align_batch(mb["ref"].ctypes.data, mb["query"].ctypes.data, od[:k].ctypes.data, k,
-                                                *SCORES, TILE - OVERLAP, cores, None)
+                                                *SCORES, TILE - OVERLAP, cores, scores.ctypes.data)
         else:
-            O.align_batch(mb["ref"], mb["query"], od[:k], scores=SCORES, et=TILE - OVERLAP, max_len=TILE, n_threads=cores)
+            res, _ = O.align_batch(mb["ref"], mb["query"], od[:k], scores=SCORES, et=TILE - OVERLAP, max_len=TILE,
+                                   n_threads=cores)
+            scores[:k] = res["score"]
             cells = int((od["ref_len"][:k].astype(np.int64) * od["query_len"][:k]).sum())
         return cells, time.perf_counter() - t0
 
@@ -147,6 +151,8 @@ def cpu_arm(args, mb, seconds):
     c0, t0 = run(k0)                                   # calibration (also warms the allocator)
     k = int(min(n, max(k0, k0 * seconds / max(t0, 1e-3))))
     cells, t = run(k)
+    if gpu_scores is not None and not (scores[:k] == gpu_scores[:k]).all():
+        raise SystemExit("bench: GPU tile scores differ from the CPU checker on the baseline sample")
     return {"value": cells / t / 1e9, "unit": UNIT, "cores": cores, "kind": "reference" if use_ref else "port",
             "sample": f"{k} tiles of the same batch ({cells / 1e9:.2f} G cells) in {t:.1f} s, "
                       f"{'reference AlignWithBT (align.cpp:60-233) via oracle/_ref' if use_ref else 'oracle C port'}, "
@@ -315,7 +321,7 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
         if world == 1 and not args.no_cpu_baseline:
             small = {k: (v[:1 << 15] if k not in ("ref", "query") else v) for k, v in mb.items()}
-            line["cpu_baseline"] = {k: v for k, v in cpu_arm(args, small, args.cpu_seconds).items()
+            line["cpu_baseline"] = {k: v for k, v in cpu_arm(args, small, args.cpu_seconds, res_dev["score"]).items()
                                     if k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     eng.close()

@@ -26,6 +26,8 @@ struct KParams {
     int tile_size;
     int win_rows;            // rows of direction codes kept per tile (<= et + 1)
     int win_lanes;           // lanes (column strips) of direction codes kept
+    int s16_bias;            // packed kernel: bias of the x16 domain
+    int one;                 // 1, opaque to the compiler (IMAD-as-add on the FMA pipe)
     SeqSetDev sets[GACT_MAX_SETS];
 };
 

@@ -70,38 +70,69 @@ struct DirWin16 {
     }
 };
 
-// traceback, align.cpp:185-230, one lane.  v = score of the current state's cell.
+// traceback, align.cpp:185-230, one lane.  v = score of the current state's cell;
+// the window position (entry e, column c inside the strip, half) is kept incrementally.
 template <int CS>
-__device__ __forceinline__ void traceback_tile16(const DirWin16<CS> &dw, const uint32_t *rr, const uint16_t *qs,
+__device__ __forceinline__ void traceback_tile16(const DirWin16<CS> &dw, const uint16_t *rb, const uint16_t *qs,
                                                  int n, int m, int score, const KParams &P,
                                                  uint32_t *states, gact_tile_result *res,
                                                  int out_max_i, int out_max_j)
 {
-    int i = n, j = m, is = 0, js = 0, cnt = 0, v = score;
-    const int et = P.et;
+    constexpr int NW = DirWin16<CS>::NW;
+    int i = n, j = m, cnt = 0, v = score;
+    const int et = P.et, nl = dw.nl;
+    int ri = et, rj = et;                       // remaining step budget per dimension
     uint32_t acc = 0;
-    int state = (i > 0 && j > 0 && v > 0) ? (dw.load(i, j) >> 2) : 0;
-    while (state != 0) {
-        if (is >= et || js >= et) break;
-        if (i <= 0 || j <= 0) break;
+    // window cursor
+    int s = (j > 0) ? (j - 1) / CS : 0;
+    int c = (j - 1) - s * CS, half = s & 1;
+    int e = (i + half - dw.i0) * nl + ((s >> 1) - dw.lane0);
+    auto fetch = [&]() -> int {
+        uint32_t x;
+        if (DirWin16<CS>::HAS_B) {
+            const uint32_t wv = dw.w[e * NW + ((c >> 2) < NW ? (c >> 2) : 0)], bv = dw.b[e];
+            x = (c < NW * 4) ? (wv >> (16 * half + 12 - 4 * (c & 3))) : (bv >> (4 * half));
+        } else {
+            x = dw.w[e * NW + (c >> 2)] >> (16 * half + 12 - 4 * (c & 3));
+        }
+        return (int)(x & 15u);
+    };
+    auto dec_j = [&]() {
+        j--; c--;
+        const bool wrap = c < 0;
+        const int de = half ? -nl : nl - 1;
+        c = wrap ? CS - 1 : c;
+        e += wrap ? de : 0;
+        half ^= (int)wrap;
+    };
+    int code = (i > 0 && j > 0) ? fetch() : 0;
+    int state = (v > 0) ? (code >> 2) : 0;
+    if (i <= 0 || j <= 0) state = 0;
+    while (state != 0 && ri > 0 && rj > 0) {
         acc |= (uint32_t)state << (2 * (cnt & 15));
         if ((cnt & 15) == 15) { states[cnt >> 4] = acc; acc = 0; }
         cnt++;
         if (state == 3) {
-            const int s = ((rr[i] & 0xffffu) == qs[j]) ? P.match : P.mismatch;
-            v -= s;                                   // H[i-1][j-1] = M[i][j] - s   (M > 0 on the path)
-            i--; j--; is++; js++;
-            state = (i > 0 && j > 0 && v > 0) ? (dw.load(i, j) >> 2) : 0;
+            const int sc = (rb[i] == qs[j]) ? P.match : P.mismatch;
+            v -= sc;                                  // H[i-1][j-1] = M[i][j] - s   (M > 0 on the path)
+            i--; e -= nl; ri--;
+            dec_j(); rj--;
+            code = fetch();
+            state = (i > 0 && j > 0 && v > 0) ? (code >> 2) : 0;
         } else if (state == 2) {
-            const bool open = dw.load(i, j) & 2;
+            const bool open = code & 2;
             v -= open ? P.gap_open : P.gap_extend;
             state = open ? 3 : 2;
-            i--; is++;
+            i--; e -= nl; ri--;
+            code = fetch();
+            if (i <= 0) state = 0;                    // unreachable for gap scores <= 0
         } else {
-            const bool open = dw.load(i, j) & 1;
+            const bool open = code & 1;
             v -= open ? P.gap_open : P.gap_extend;
             state = open ? 3 : 1;
-            j--; js++;
+            dec_j(); rj--;
+            code = fetch();
+            if (j <= 0) state = 0;
         }
     }
     if (cnt & 15) states[cnt >> 4] = acc;
@@ -109,11 +140,32 @@ __device__ __forceinline__ void traceback_tile16(const DirWin16<CS> &dw, const u
     res->max_i = out_max_i;
     res->max_j = out_max_j;
     res->n_states = cnt;
-    res->i_steps = is;
-    res->j_steps = js;
+    res->i_steps = et - ri;
+    res->j_steps = et - rj;
 }
 
-template <int CS>
+// substitution score of one column pair.
+//   LUT mode (both sets 2-bit packed, |score*16| < 128): one PRMT -- the row registers hold a
+//     4-byte table (score*16 per query code) for the low and the high strip's reference base,
+//     the per-column selector picks byte [code] and its sign extension for each half;
+//   general mode: HSET2 equality mask on fp16-encoded raw bytes + one LOP3 select.
+template <bool LUT>
+__device__ __forceinline__ uint32_t subst_score(uint32_t qc, uint32_t rlo, uint32_t rhi, uint32_t ma16, uint32_t mi16)
+{
+    if (LUT) {
+        // prmt in its default mode: selector bit 3 of a nibble replicates the selected byte's sign
+        // (__byte_perm would mask that bit away)
+        uint32_t r;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(rlo), "r"(rhi), "r"(qc));
+        return r;
+    }
+    const __half2 qh = *reinterpret_cast<const __half2 *>(&qc);
+    const __half2 rh = *reinterpret_cast<const __half2 *>(&rlo);
+    const uint32_t eq = __heq2_mask(qh, rh);
+    return (eq & ma16) | (~eq & mi16);
+}
+
+template <int CS, bool LUT>
 __global__ void __launch_bounds__(256)
 gact_tile_s16_kernel(const __grid_constant__ KParams P, const gact_tile_desc *__restrict__ descs,
                      int n_tiles, const EffLen *__restrict__ eff,
@@ -121,22 +173,34 @@ gact_tile_s16_kernel(const __grid_constant__ KParams P, const gact_tile_desc *__
                      int pitch_words, int *counter, size_t per_warp_bytes)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int lane = threadIdx.x & 31;
+    int lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
     const int warp = threadIdx.x >> 5;
     constexpr int TS = CS * 64;
     constexpr int NW = DirWin16<CS>::NW;
 
-    // per-warp carve-out: rr[TS+2] words | qs[TS+2] halves | direction window
+    // per-warp carve-out: rr[TS+2] words | qs[TS+2] halves | rb[TS+2] halves | direction window
+    //   general mode: rr[i] = enc(R[i]) | enc(R[i-1]) << 16;  LUT mode: rr[i] = score table of R[i]
+    //   (the traceback needs raw equality: it uses rb[] / qs[])
     uint8_t *my = smem + (size_t)warp * per_warp_bytes;
-    uint32_t *rr = reinterpret_cast<uint32_t *>(my);                 // rr[i] = enc(R[i]) | enc(R[i-1]) << 16
-    uint16_t *qs = reinterpret_cast<uint16_t *>(my + (TS + 2) * 4);  // qs[j] = enc(Q[j])
-    void *dirbase = my + (TS + 2) * 4 + (((TS + 2) * 2 + 15) & ~15);
+    uint32_t *rr = reinterpret_cast<uint32_t *>(my);
+    uint16_t *qs = reinterpret_cast<uint16_t *>(my + (TS + 2) * 4);               // qs[j] = enc(Q[j])
+    uint16_t *rb = reinterpret_cast<uint16_t *>(my + (TS + 2) * 6);               // rb[i] = enc(R[i])
+    void *dirbase = my + (((TS + 2) * 8 + 15) & ~15);
 
+    // biased x16 domain: stored = 16*score + tag + B; B keeps every half-word that takes part in a
+    // plain 32-bit add non-negative, so those adds can run as IMAD on the FMA pipe
+    const int B = P.s16_bias;
+    const uint32_t Bp = pk16(B);
     const uint32_t ma16 = pk16(P.match * 16), mi16 = pk16(P.mismatch * 16);
     const uint32_t ge16 = pk16(P.gap_extend * 16);
-    const uint32_t goI = pk16(P.gap_open * 16 - 2);      // M tag 1100 -> I-open tag 1010
-    const uint32_t goD = pk16(P.gap_open * 16 - 7);      // M tag 1100 -> D-open tag 0101
-    const uint32_t CLEAN = 0xfff0fff0u, TAGM = 0x000c000cu;
+    const int KO = (P.gap_open * 16) * 65537;            // + go            (phase 1, untagged)
+    const int KI = (P.gap_open * 16 - 5) * 65537;        // M tag 1111 -> I-open tag 1010
+    const int KD = (P.gap_open * 16 - 10) * 65537;       // M tag 1111 -> D-open tag 0101
+    const int ONE = P.one;                               // opaque 1: keeps the adds on IMAD
+    const uint32_t borderD_tag = ((uint32_t)(B + P.gap_open * 16 + 5) << 16) | (uint32_t)B;   // lane 0: G = 0 | D[i][1] = go, open
+    const uint32_t borderD_raw = ((uint32_t)(B + P.gap_open * 16) << 16) | (uint32_t)B;
+    const uint32_t lut_mis = (uint32_t)((P.mismatch * 16) & 0xff) * 0x01010101u;
 
     for (;;) {
         int t = 0;
@@ -152,9 +216,21 @@ gact_tile_s16_kernel(const __grid_constant__ KParams P, const gact_tile_desc *__
 
         __syncwarp();
         for (int x = lane; x <= n + 1; x += 32) {
-            const uint32_t cur = (x >= 1 && x <= n) ? enc_base(tile_base(rset, d.ref_off, d.ref_len, d.reverse, x)) : SENT_R;
-            const uint32_t prv = (x >= 2 && x <= n + 1) ? enc_base(tile_base(rset, d.ref_off, d.ref_len, d.reverse, x - 1)) : SENT_R;
-            rr[x] = cur | (prv << 16);
+            const bool in = (x >= 1 && x <= n);
+            const int base = in ? tile_base(rset, d.ref_off, d.ref_len, d.reverse, x) : 0;
+            rb[x] = (uint16_t)(in ? enc_base(base) : SENT_R);
+            if (LUT) {
+                // byte [code] = match*16 where code == base's 2-bit code, mismatch*16 elsewhere
+                const int code = (base == 'A') ? 0 : (base == 'C') ? 1 : (base == 'G') ? 2 : (base == 'T') ? 3 : 4;
+                uint32_t w = lut_mis;
+                if (in && code < 4) w ^= (uint32_t)(((P.match ^ P.mismatch) * 16) & 0xff) << (8 * code);
+                rr[x] = w;
+            }
+        }
+        if (!LUT) {
+            __syncwarp();
+            for (int x = lane; x <= n + 1; x += 32)
+                rr[x] = (uint32_t)rb[x] | ((uint32_t)(x >= 1 ? rb[x - 1] : (uint16_t)SENT_R) << 16);
         }
         for (int x = lane; x <= m; x += 32)
             qs[x] = (x >= 1) ? (uint16_t)enc_base(tile_base(qset, d.query_off, d.query_len, d.reverse, x)) : (uint16_t)SENT_Q;
@@ -164,88 +240,127 @@ gact_tile_s16_kernel(const __grid_constant__ KParams P, const gact_tile_desc *__
 #pragma unroll
         for (int c = 0; c < CS; c++) {
             const int jl = (2 * lane) * CS + c + 1, jh = (2 * lane + 1) * CS + c + 1;
-            q[c] = (jl <= m ? (uint32_t)qs[jl] : SENT_Q + c) | ((jh <= m ? (uint32_t)qs[jh] : SENT_Q + c) << 16);
+            const uint32_t el = jl <= m ? (uint32_t)qs[jl] : SENT_Q + c, eh = jh <= m ? (uint32_t)qs[jh] : SENT_Q + c;
+            if (LUT) {
+                // ASCII A=0x41 C=0x43 G=0x47 T=0x54: (b >> 1) & 3 = 0,1,3,2 -> 2-bit code 0,1,2,3
+                const uint32_t tl = (el >> 1) & 3u, th = (eh >> 1) & 3u;
+                const uint32_t l2 = (jl <= m) ? (tl ^ (tl >> 1)) : 0u, h2 = (jh <= m) ? (th ^ (th >> 1)) : 0u;
+                q[c] = l2 | ((8u | l2) << 4) | ((4u | h2) << 8) | ((12u | h2) << 12);
+            } else {
+                q[c] = el | (eh << 16);
+            }
         }
 
         DirWin16<CS> dw;
         dw.init(dirbase, n, m, P);
         const int laststrip = (m > 0) ? (m - 1) / CS : -1;
         const int lastlane = laststrip >> 1;
-        // where the corner H[n][m] will appear
-        const int c_lane = lastlane, c_half = laststrip & 1, c_col = (m > 0) ? (m - 1) - laststrip * CS : 0;
+        // the corner H[n][m] appears in lane c_lane, half c_half, column c_col, at step kc
+        const int c_lane = max(lastlane, 0), c_half = laststrip & 1, c_col = (m > 0) ? (m - 1) - laststrip * CS : 0;
+        const int kc = n + 2 * c_lane + c_half;
+        const int steps = (n > 0 && m > 0) ? n + 1 + 2 * lastlane : 0;
+        // lane-private step windows: active for k in [kfirst, kfirst + n], stores from kstore on
+        const int kfirst = (lane <= lastlane) ? 2 * lane + 1 : 0x3fffffff;
+        const int kstore = (lane >= dw.lane0) ? dw.i0 + 2 * lane : 0x3fffffff;
+        const uint32_t *rrp = rr - 2 * lane;             // rrp[k] = rr[k - 2*lane]
 
-        // state before the lane's first step: low half = border row 0 already applied,
-        // high half = "row -1" (its first step is the pseudo row 0)
+        // ---------------- phase 1: rows above the traceback window, score only ----------------
+        // untagged biased values; low half = after border row 0, high half = "row -1"
         uint32_t Gup[CS], IoUp[CS], IcUp[CS];
 #pragma unroll
         for (int c = 0; c < CS; c++) {
-            Gup[c] = 0;
-            IoUp[c] = pk16(P.gap_open * 16 + 10, S16_NEG);      // (0|1100) + go16 - 2
-            IcUp[c] = pk16(S16_NEG + 8, S16_NEG + 8);
+            Gup[c] = Bp;
+            IoUp[c] = pk16(B + P.gap_open * 16, S16_NEG);      // M[0][j] + go
+            IcUp[c] = pk16(S16_NEG, S16_NEG);
         }
-        uint32_t eG = 0;                                   // G of my last column (row just finished)
-        uint32_t eD = pk16(S16_NEG + 4);                   // D value for the column right of my strip
-        uint32_t diag = 0;                                 // G[i-1][first column - 1] for both halves
-        const uint32_t borderD = pk16(P.gap_open * 16 + 5);  // D[i][1] = 0 + go, open flag set
-        int corner16 = 0;
-
-        const int steps = (n > 0 && m > 0) ? n + 1 + 2 * lastlane : 0;
-        for (int k = 1; k <= steps; k++) {
-            const int ilo = k - 2 * lane;                  // low half: row ilo, high half: row ilo-1
-            // edge of the strip to the left: low half <- lane-1's high strip, high half <- my low strip
-            const uint32_t pack = __byte_perm(eG, eD, 0x7632);          // (eG.hi, eD.hi)
+        uint32_t eG = Bp, eD = pk16(S16_NEG), diag = Bp;
+        const int k1 = min(dw.i0 - 1, steps);                  // phase 1 covers steps 1..k1 (all rows < i0)
+        int k = 1;
+        for (; k <= k1; k++) {
+            const uint32_t pack = __byte_perm(eG, eD, 0x7632);
             uint32_t recv = __shfl_up_sync(FULL, pack, 1);
-            if (lane == 0) recv = (borderD << 16);                       // G border 0, D border
-            const uint32_t inG = __byte_perm(recv, eG, 0x5410);          // lo: recv.lo16 (G), hi: my eG.lo
-            const uint32_t inD = __byte_perm(recv, eD, 0x5432);          // lo: recv.hi16 (D), hi: my eD.lo
-            if (ilo >= 1 && ilo <= n + 1 && lane <= lastlane) {
-                const uint32_t rp = rr[ilo];
-                const __half2 rh = *reinterpret_cast<const __half2 *>(&rp);
+            if (lane == 0) recv = borderD_raw;
+            const uint32_t inG = __byte_perm(recv, eG, 0x5410);
+            const uint32_t inD = __byte_perm(recv, eD, 0x5432);
+            if ((unsigned)(k - kfirst) <= (unsigned)n) {
+                const uint32_t rlo = rrp[k], rhi = LUT ? rrp[k - 1] : 0u;
+                uint32_t hd = diag, dv = inD;
+#pragma unroll
+                for (int c = 0; c < CS; c++) {
+                    const uint32_t sc = subst_score<LUT>(q[c], rlo, rhi, ma16, mi16);
+                    const uint32_t mc = __viaddmax_s16x2(hd, sc, Bp);
+                    hd = Gup[c];
+                    const uint32_t iv = __viaddmax_s16x2(IcUp[c], ge16, IoUp[c]);
+                    Gup[c] = __vimax3_s16x2(mc, iv, dv);
+                    const uint32_t mo = (uint32_t)((int)mc * ONE + KO);
+                    IoUp[c] = mo;
+                    IcUp[c] = iv;
+                    dv = __viaddmax_s16x2(dv, ge16, mo);
+                }
+                eG = Gup[CS - 1];
+                eD = dv;
+                diag = inG;
+            }
+        }
+        // ---------------- switch to the tagged domain ----------------
+#pragma unroll
+        for (int c = 0; c < CS; c++) {
+            IoUp[c] = __vadd2(IoUp[c], pk16(10));              // (M|1111) + go - 5
+            IcUp[c] = __vadd2(IcUp[c], pk16(8));               // I tag 1000
+        }
+        eD = __vadd2(eD, pk16(4));                             // D tag 0100 (flag irrelevant above the window)
+
+        // ---------------- phase 2: window rows, tagged values + direction codes ----------------
+        uint32_t *wptr = dw.w + ((k - 2 * lane - dw.i0) * dw.nl + (lane - dw.lane0)) * NW;
+        uint8_t *bptr = dw.b + ((k - 2 * lane - dw.i0) * dw.nl + (lane - dw.lane0));
+        int corner16 = B;
+        for (; k <= steps; k++) {
+            const uint32_t pack = __byte_perm(eG, eD, 0x7632);           // (eG.hi, eD.hi)
+            uint32_t recv = __shfl_up_sync(FULL, pack, 1);
+            if (lane == 0) recv = borderD_tag;
+            const uint32_t inG = __byte_perm(recv, eG, 0x5410);          // lo: left strip's G, hi: my low strip's G
+            const uint32_t inD = __byte_perm(recv, eD, 0x5432);          // same for D
+            if ((unsigned)(k - kfirst) <= (unsigned)n) {
+                const uint32_t rlo = rrp[k], rhi = LUT ? rrp[k - 1] : 0u;
                 uint32_t hd = diag, dv = inD;
                 uint32_t acc[NW + 1];
 #pragma unroll
                 for (int c = 0; c < CS; c++) {
-                    const __half2 qh = *reinterpret_cast<const __half2 *>(&q[c]);
-                    const uint32_t eq = __heq2_mask(qh, rh);
-                    const uint32_t s = (eq & ma16) | (~eq & mi16);
-                    const uint32_t mraw = __viaddmax_s16x2_relu(hd, s, 0);
-                    const uint32_t mt = (mraw & CLEAN) | TAGM;
+                    const uint32_t sc = subst_score<LUT>(q[c], rlo, rhi, ma16, mi16);
+                    const uint32_t mt = __viaddmax_s16x2(hd, sc, Bp) | 0x000f000fu;     // M, tag 1111
                     hd = Gup[c];
                     const uint32_t iv = __viaddmax_s16x2(IcUp[c], ge16, IoUp[c]);
                     const uint32_t g = __vimax3_s16x2(mt, iv, dv);
                     const uint32_t code = (g & 0x000c000cu) | ((iv | dv) & 0x00030003u);
                     if ((c & 3) == 0) acc[c >> 2] = code; else acc[c >> 2] = acc[c >> 2] * 16u + code;
                     Gup[c] = g;
-                    IoUp[c] = __vadd2(mt, goI);
+                    IoUp[c] = (uint32_t)((int)mt * ONE + KI);
                     IcUp[c] = iv & 0xfffdfffdu;
-                    // D of the next column (or of the neighbouring strip's first column)
-                    dv = __viaddmax_s16x2(dv & 0xfffefffeu, ge16, __vadd2(mt, goD));
+                    dv = __viaddmax_s16x2(dv & 0xfffefffeu, ge16, (uint32_t)((int)mt * ONE + KD));
                 }
                 eG = Gup[CS - 1];
                 eD = dv;
                 diag = inG;
-                if (lane == c_lane) {
-                    const int irow = ilo - c_half;
-                    if (irow == n) {
-                        uint32_t gsel = 0;
+                if (k >= kstore) {
 #pragma unroll
-                        for (int c = 0; c < CS; c++) if (c == c_col) gsel = Gup[c];
-                        corner16 = (int)(short)(c_half ? (gsel >> 16) : (gsel & 0xffffu));
-                    }
-                }
-                if (ilo >= dw.i0 && lane >= dw.lane0) {
-                    const int e = (ilo - dw.i0) * dw.nl + (lane - dw.lane0);
-#pragma unroll
-                    for (int x = 0; x < NW; x++) dw.w[e * NW + x] = acc[x];
-                    if (DirWin16<CS>::HAS_B) dw.b[e] = (uint8_t)((acc[NW] & 15u) | ((acc[NW] >> 12) & 0xf0u));
+                    for (int x = 0; x < NW; x++) wptr[x] = acc[x];
+                    if (DirWin16<CS>::HAS_B) *bptr = (uint8_t)((acc[NW] & 15u) | ((acc[NW] >> 12) & 0xf0u));
                 }
             }
+            wptr += dw.nl * NW;
+            bptr += dw.nl;
+            if (k == kc) {                                   // warp-uniform: the corner row just finished
+                uint32_t gsel = 0;
+#pragma unroll
+                for (int c = 0; c < CS; c++) if (c == c_col) gsel = Gup[c];
+                corner16 = (int)(short)(c_half ? (gsel >> 16) : (gsel & 0xffffu));
+            }
         }
-        int corner = __shfl_sync(FULL, corner16, max(c_lane, 0)) >> 4;
+        int corner = (__shfl_sync(FULL, corner16, c_lane) - B) >> 4;
         if (n == 0 || m == 0) corner = 0;
         __syncwarp();
         if (lane == 0) {
-            traceback_tile16<CS>(dw, rr, qs, n, m, corner, P, states + (size_t)t * pitch_words, &results[t],
+            traceback_tile16<CS>(dw, rb, qs, n, m, corner, P, states + (size_t)t * pitch_words, &results[t],
                                  d.first ? n : d.ref_len, d.first ? m : d.query_len);
         }
         __syncwarp();
@@ -258,17 +373,17 @@ template <int CS>
 inline size_t s16_warp_bytes(int win_rows, int win_lanes)
 {
     constexpr int TS = CS * 64;
-    return (size_t)(TS + 2) * 4 + (((TS + 2) * 2 + 15) & ~15) + DirWin16<CS>::bytes(win_rows, win_lanes);
+    return (size_t)(((TS + 2) * 8 + 15) & ~15) + DirWin16<CS>::bytes(win_rows, win_lanes);
 }
 
 typedef void (*s16_fn)(const KParams, const gact_tile_desc *, int, const EffLen *, gact_tile_result *,
                        uint32_t *, int, int *, size_t);
-inline s16_fn s16_pick(int CS)
+inline s16_fn s16_pick(int CS, bool lut)
 {
     switch (CS) {
-        case 4: return gact_tile_s16_kernel<4>;
-        case 5: return gact_tile_s16_kernel<5>;
-        case 8: return gact_tile_s16_kernel<8>;
+        case 4: return lut ? gact_tile_s16_kernel<4, true> : gact_tile_s16_kernel<4, false>;
+        case 5: return lut ? gact_tile_s16_kernel<5, true> : gact_tile_s16_kernel<5, false>;
+        case 8: return lut ? gact_tile_s16_kernel<8, true> : gact_tile_s16_kernel<8, false>;
         default: return nullptr;
     }
 }
@@ -276,7 +391,8 @@ inline s16_fn s16_pick(int CS)
 // win_rows/win_lanes for the s16 kernel are derived here (they differ from the int32 kernel's).
 struct S16Plan {
     bool ok = false;
-    int CS = 0, win_rows = 0, win_lanes = 0, warps_per_cta = 0, ctas = 0;
+    int CS = 0, win_rows = 0, win_lanes = 0, warps_per_cta = 0, ctas = 0, bias = 0;
+    bool lut_ok = false;      // scores fit the one-PRMT substitution table
     size_t per_warp_bytes = 0, smem = 0;
 };
 
@@ -285,7 +401,10 @@ inline int s16_make_plan(const gact_params &p, int num_sms, S16Plan *pl)
     *pl = S16Plan();
     const int T = p.tile_size, et = p.tile_size - p.tile_overlap;
     // value range of the x16 tagged domain and the pseudo-row trick
-    const long hi = (long)T * (p.match > 0 ? p.match : 0) * 16 + 16;
+    const int bias = 16 * (-p.gap_open + 2);
+    pl->bias = bias;
+    pl->lut_ok = (p.match * 16 <= 127 && p.mismatch * 16 >= -128);
+    const long hi = (long)T * (p.match > 0 ? p.match : 0) * 16 + 16 + bias;
     if (hi > 30000 || p.mismatch > 0 || p.match < 0 || p.gap_open < -500 || p.gap_extend < -500 || p.mismatch < -1000)
         return 0;
     int CS;
@@ -317,7 +436,8 @@ inline int s16_make_plan(const gact_params &p, int num_sms, S16Plan *pl)
     pl->warps_per_cta = best_w;
     pl->ctas = best_c * num_sms;
     pl->smem = (size_t)best_w * pw;
-    if (cudaFuncSetAttribute((const void *)s16_pick(CS), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem) != cudaSuccess)
+    if (cudaFuncSetAttribute((const void *)s16_pick(CS, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem) != cudaSuccess ||
+        cudaFuncSetAttribute((const void *)s16_pick(CS, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem) != cudaSuccess)
         return -1;
     pl->ok = true;
     return 0;
@@ -328,10 +448,15 @@ inline void s16_launch(const S16Plan &pl, KParams kp, const gact_tile_desc *desc
 {
     kp.win_rows = pl.win_rows;
     kp.win_lanes = pl.win_lanes;
+    kp.s16_bias = pl.bias;
+    kp.one = 1;
+    // one-PRMT substitution table only when every set in use is 2-bit packed (ACGT only)
+    bool lut = pl.lut_ok;
+    for (int i = 0; i < GACT_MAX_SETS; i++) if (kp.sets[i].bytes) lut = false;
     int ctas = pl.ctas;
     const int need = (n + pl.warps_per_cta - 1) / pl.warps_per_cta;
     if (need < ctas) ctas = need;
-    s16_pick(pl.CS)<<<ctas, pl.warps_per_cta * 32, pl.smem, st>>>(kp, descs, n, eff, results, states, pitch_words,
+    s16_pick(pl.CS, lut)<<<ctas, pl.warps_per_cta * 32, pl.smem, st>>>(kp, descs, n, eff, results, states, pitch_words,
                                                                   counter, pl.per_warp_bytes);
 }
 
