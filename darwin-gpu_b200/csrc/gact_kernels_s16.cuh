@@ -70,78 +70,77 @@ struct DirWin16 {
     }
 };
 
-// traceback, align.cpp:185-230, one lane.  v = score of the current state's cell;
-// the window position (entry e, column c inside the strip, half) is kept incrementally.
+// traceback, align.cpp:185-230, by the whole warp.  All lanes hold the same cursor
+// (i, j, state, v = score of the current state's cell, remaining step budgets).
+//   * state M: the 32 lanes look at the 32 cells down the diagonal at once -- lane t loads the
+//     code of cell (i-t, j-t) and the match bit of that cell; the scores along the diagonal follow
+//     from a ballot + popc, so the length of the M run (the common case: ~85 % of all states) is
+//     one ffs away.  Up to 31 states are emitted per iteration.
+//   * states I / D: one step per iteration (gap runs are short).
+// States are first written one byte each into stbuf (shared memory), then packed 16 per word.
 template <int CS>
 __device__ __forceinline__ void traceback_tile16(const DirWin16<CS> &dw, const uint16_t *rb, const uint16_t *qs,
+                                                 uint8_t *stbuf, int lane,
                                                  int n, int m, int score, const KParams &P,
                                                  uint32_t *states, gact_tile_result *res,
                                                  int out_max_i, int out_max_j)
 {
-    constexpr int NW = DirWin16<CS>::NW;
+    const int et = P.et, ma = P.match, mi = P.mismatch, go = P.gap_open, ge = P.gap_extend;
+    const int i0 = dw.i0, j0 = max(m - et, 1);
     int i = n, j = m, cnt = 0, v = score;
-    const int et = P.et, nl = dw.nl;
     int ri = et, rj = et;                       // remaining step budget per dimension
-    uint32_t acc = 0;
-    // window cursor
-    int s = (j > 0) ? (j - 1) / CS : 0;
-    int c = (j - 1) - s * CS, half = s & 1;
-    int e = (i + half - dw.i0) * nl + ((s >> 1) - dw.lane0);
-    auto fetch = [&]() -> int {
-        uint32_t x;
-        if (DirWin16<CS>::HAS_B) {
-            const uint32_t wv = dw.w[e * NW + ((c >> 2) < NW ? (c >> 2) : 0)], bv = dw.b[e];
-            x = (c < NW * 4) ? (wv >> (16 * half + 12 - 4 * (c & 3))) : (bv >> (4 * half));
-        } else {
-            x = dw.w[e * NW + (c >> 2)] >> (16 * half + 12 - 4 * (c & 3));
-        }
-        return (int)(x & 15u);
-    };
-    auto dec_j = [&]() {
-        j--; c--;
-        const bool wrap = c < 0;
-        const int de = half ? -nl : nl - 1;
-        c = wrap ? CS - 1 : c;
-        e += wrap ? de : 0;
-        half ^= (int)wrap;
-    };
-    int code = (i > 0 && j > 0) ? fetch() : 0;
-    int state = (v > 0) ? (code >> 2) : 0;
-    if (i <= 0 || j <= 0) state = 0;
+    int state = (i > 0 && j > 0 && v > 0) ? (dw.load(i, j) >> 2) : 0;
     while (state != 0 && ri > 0 && rj > 0) {
-        acc |= (uint32_t)state << (2 * (cnt & 15));
-        if ((cnt & 15) == 15) { states[cnt >> 4] = acc; acc = 0; }
-        cnt++;
         if (state == 3) {
-            const int sc = (rb[i] == qs[j]) ? P.match : P.mismatch;
-            v -= sc;                                  // H[i-1][j-1] = M[i][j] - s   (M > 0 on the path)
-            i--; e -= nl; ri--;
-            dec_j(); rj--;
-            code = fetch();
-            state = (i > 0 && j > 0 && v > 0) ? (code >> 2) : 0;
-        } else if (state == 2) {
-            const bool open = code & 2;
-            v -= open ? P.gap_open : P.gap_extend;
-            state = open ? 3 : 2;
-            i--; e -= nl; ri--;
-            code = fetch();
-            if (i <= 0) state = 0;                    // unreachable for gap scores <= 0
+            const int it = i - lane, jt = j - lane;
+            const bool inb = (it >= i0 && jt >= j0);
+            const int code_t = inb ? dw.load(it, jt) : 0;
+            const bool match_t = inb && (rb[it] == qs[jt]);
+            const unsigned mm = __ballot_sync(FULL, match_t);
+            const int below = __popc(mm & ((1u << lane) - 1u));
+            const int v_t = v - (below * ma + (lane - below) * mi);        // H of cell t, if cells 0..t-1 are all M
+            const bool isM_t = (lane == 0) || (inb && v_t > 0 && (code_t >> 2) == 3);
+            const unsigned run = __ballot_sync(FULL, isM_t);
+            int L = __ffs(~run) - 1;                                        // leading M cells
+            if (L < 0 || L > 31) L = 31;                                    // cell L must be covered by lane L
+            L = min(L, min(ri, rj));
+            if (lane < L) stbuf[cnt + lane] = 3;
+            cnt += L; ri -= L; rj -= L;
+            const int bl = __popc(mm & ((1u << L) - 1u));
+            v -= bl * ma + (L - bl) * mi;
+            i -= L; j -= L;
+            const int codeL = __shfl_sync(FULL, code_t, L);
+            state = (i >= i0 && j >= j0 && v > 0) ? (codeL >> 2) : 0;
         } else {
-            const bool open = code & 1;
-            v -= open ? P.gap_open : P.gap_extend;
-            state = open ? 3 : 1;
-            dec_j(); rj--;
-            code = fetch();
-            if (j <= 0) state = 0;
+            const int code = dw.load(i, j);
+            const bool open = (state == 2) ? (code & 2) : (code & 1);
+            if (lane == 0) stbuf[cnt] = (uint8_t)state;
+            cnt++;
+            v -= open ? go : ge;
+            if (state == 2) { i--; ri--; } else { j--; rj--; }
+            state = open ? 3 : state;
+            if (i <= 0 || j <= 0) state = 0;                                // unreachable for gap scores <= 0
         }
     }
-    if (cnt & 15) states[cnt >> 4] = acc;
-    res->score = score;
-    res->max_i = out_max_i;
-    res->max_j = out_max_j;
-    res->n_states = cnt;
-    res->i_steps = et - ri;
-    res->j_steps = et - rj;
+    __syncwarp();
+    for (int w = lane; w * 16 < cnt; w += 32) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int x = 0; x < 16; x++) {
+            const int idx = w * 16 + x;
+            const uint32_t st = (idx < cnt) ? stbuf[idx] : 0u;
+            acc |= st << (2 * x);
+        }
+        states[w] = acc;
+    }
+    if (lane == 0) {
+        res->score = score;
+        res->max_i = out_max_i;
+        res->max_j = out_max_j;
+        res->n_states = cnt;
+        res->i_steps = et - ri;
+        res->j_steps = et - rj;
+    }
 }
 
 // substitution score of one column pair.
@@ -359,10 +358,10 @@ gact_tile_s16_kernel(const __grid_constant__ KParams P, const gact_tile_desc *__
         int corner = (__shfl_sync(FULL, corner16, c_lane) - B) >> 4;
         if (n == 0 || m == 0) corner = 0;
         __syncwarp();
-        if (lane == 0) {
-            traceback_tile16<CS>(dw, rb, qs, n, m, corner, P, states + (size_t)t * pitch_words, &results[t],
-                                 d.first ? n : d.ref_len, d.first ? m : d.query_len);
-        }
+        // rr[] (substitution tables) is dead now: reuse it as the per-state byte buffer (2*et <= 4*(TS+2))
+        traceback_tile16<CS>(dw, rb, qs, reinterpret_cast<uint8_t *>(rr), lane, n, m, corner, P,
+                             states + (size_t)t * pitch_words, &results[t],
+                             d.first ? n : d.ref_len, d.first ? m : d.query_len);
         __syncwarp();
     }
 }
