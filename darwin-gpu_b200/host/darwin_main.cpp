@@ -1,0 +1,287 @@
+// darwin_main.cpp -- drop-in `darwin` command line on top of the B200 GACT engine.
+//
+//   ./darwin <REFERENCE>.fasta <READS>.fasta CPU_THREADS [NUM_BLOCKS THREADS_PER_BLOCK]
+//
+// Same surface as the reference (darwin.cpp:451-646, README:17-22): params.cfg in the
+// working directory, positional arguments, `darwin.<tid>.out` overlap files, the
+// "num_candidates: F R" and phase-time lines on stdout.  NUM_BLOCKS / THREADS_PER_BLOCK
+// are accepted and ignored (the engine sizes its own persistent grid).  Additional
+// controls come from the environment so that the reference form keeps working:
+//   DARWIN_GPUS=<n>      GPUs to use (default: all visible); reads are sharded contiguously
+//                        by ceil(num_reads / n), one host scheduler thread + engine per GPU
+//   DARWIN_KERNEL=<0|1|2> kernel variant (auto / int32 / s16x2)
+//
+// Flow per GPU shard: D-SOFT on the host for every read of the shard (CPU_THREADS / n
+// threads), then all candidates of the shard go through GactScheduler, then the overlap
+// lines are written in the reference CPU build's order (per read: forward, then reverse).
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/gact_b200.h"
+#include "darwin_config.h"
+#include "fasta_io.h"
+#include "gact_scheduler.h"
+#include "seed_table.h"
+
+using namespace darwin;
+using Clock = std::chrono::steady_clock;
+
+static long ms_since(Clock::time_point t0)
+{
+    return (long)(std::chrono::duration<double, std::milli>(Clock::now() - t0).count() + 0.5);
+}
+
+static std::mutex io_lock;
+
+struct Shard {
+    int tid = 0, device = 0;
+    size_t first_read = 0, last_read = 0;     // [first, last)
+    int dsoft_threads = 1;
+    SchedulerStats stats;
+    long dsoft_ms = 0, gact_ms = 0;
+    uint64_t cand_fwd = 0, cand_rev = 0;
+    std::string error;
+};
+
+int main(int argc, char **argv)
+{
+    if (argc < 4) {
+        fprintf(stderr, "Usage: ./darwin <REFERENCE>.fasta <READS>.fasta CPU_THREADS [NUM_BLOCKS THREADS_PER_BLOCK]\n");
+        return 1;
+    }
+    Params cfg;
+    try {
+        cfg = Params::from_file("params.cfg");
+    } catch (const std::exception &e) {
+        fprintf(stderr, "params.cfg: %s\n", e.what());
+        return 1;
+    }
+    const std::string ref_path(argv[1]), reads_path(argv[2]);
+    const int num_threads = std::max(1, atoi(argv[3]));
+    const bool same_file = (ref_path == reads_path);            // darwin.cpp:498-503
+    printf("same_file: %d\n", same_file ? 1 : 0);
+
+    int ndev = gact_device_count();
+    if (ndev <= 0) {
+        fprintf(stderr, "darwin: no CUDA device available (the GACT path has no CPU fallback)\n");
+        return 2;
+    }
+    int want_gpus = ndev;
+    if (const char *e = getenv("DARWIN_GPUS")) want_gpus = std::max(1, std::min(ndev, atoi(e)));
+    const int kernel_variant = getenv("DARWIN_KERNEL") ? atoi(getenv("DARWIN_KERNEL")) : 0;
+    printf("Using GPU: %d device(s), CPU threads: %d\n", want_gpus, num_threads);
+    printf("Scores: match = %d, mismatch = %d, gap_open = %d, gap_extend = %d\n", cfg.match, cfg.mismatch, cfg.gap_open, cfg.gap_extend);
+    printf("Minimizer window size: %d\n", (int)cfg.window_size);
+
+    // ---- reference ------------------------------------------------------------------------
+    std::cout << "\nLoading reference genome ...\n";
+    auto t0 = Clock::now();
+    FastaSet ref, reads;
+    std::string err;
+    if (!read_fasta(ref_path, &ref, &err)) { std::cerr << err << std::endl; return 1; }
+    // concatenated reference, every sequence padded with 'N' to a multiple of bin_size (darwin.cpp:530-543)
+    std::string ref_string;
+    std::vector<uint32_t> chr_start_bin(ref.seqs.size());
+    std::vector<int32_t> bin_to_chr;
+    for (size_t i = 0; i < ref.seqs.size(); i++) {
+        chr_start_bin[i] = (uint32_t)bin_to_chr.size();
+        ref_string += ref.seqs[i];
+        const size_t L = ref.seqs[i].size();
+        for (size_t b = 0; b < L / cfg.bin_size; b++) bin_to_chr.push_back((int32_t)i);
+        if (L % cfg.bin_size) {
+            ref_string.append(cfg.bin_size - L % cfg.bin_size, 'N');
+            bin_to_chr.push_back((int32_t)i);
+        }
+    }
+    const uint32_t reference_length = (uint32_t)ref_string.size();
+    std::cout << "Reference length: " << reference_length << ", " << ref.seqs.size() << " pieces" << std::endl;
+    std::cout << "Time elapsed (loading reference genome): " << ms_since(t0) << " msec" << std::endl;
+
+    // ---- reads ----------------------------------------------------------------------------
+    std::cout << "\nLoading reads ...\n";
+    t0 = Clock::now();
+    if (!read_fasta(reads_path, &reads, &err)) { std::cerr << err << std::endl; return 1; }
+    const size_t num_reads = reads.seqs.size();
+    std::vector<std::string> rev_reads(num_reads);
+    for (size_t i = 0; i < num_reads; i++) {
+        char bad = 0;
+        if (!reverse_complement(reads.seqs[i], &rev_reads[i], &bad)) {
+            std::cerr << "Bad Nt char: " << bad << std::endl;       // darwin.cpp:117-119
+            return 1;
+        }
+    }
+    std::cout << "Number of reads: " << num_reads << std::endl;
+    std::cout << "Time elapsed (loading reads): " << ms_since(t0) << " msec" << std::endl;
+
+    // ---- seed table -----------------------------------------------------------------------
+    std::cout << "\nConstructing seed position table ...\n";
+    t0 = Clock::now();
+    SeedTable *table = nullptr;
+    try {
+        table = new SeedTable(ref_string.data(), reference_length, cfg.seed_size, (uint32_t)cfg.seed_occurence_multiple,
+                              cfg.bin_size, cfg.window_size, num_threads);
+    } catch (const std::exception &e) {
+        fprintf(stderr, "seed table: %s\n", e.what());
+        return 1;
+    }
+    std::cout << "Time elapsed (seed position table construction): " << ms_since(t0) << " msec" << std::endl;
+
+    // ---- shards: contiguous read ranges, one per GPU (darwin.cpp:619-629 rule) ----------------
+    const int G = (int)std::max<size_t>(1, std::min<size_t>((size_t)want_gpus, std::max<size_t>(num_reads, 1)));
+    const size_t per = (num_reads + G - 1) / std::max(G, 1);
+    std::vector<Shard> shards;
+    for (int g = 0; g < G; g++) {
+        Shard s;
+        s.tid = g; s.device = g;
+        s.first_read = std::min(num_reads, per * g);
+        s.last_read = std::min(num_reads, per * (g + 1));
+        s.dsoft_threads = std::max(1, num_threads / G);
+        if (s.first_read < s.last_read || g == 0) shards.push_back(s);
+    }
+
+    std::vector<SeqView> ref_views(ref.seqs.size());
+    for (size_t i = 0; i < ref.seqs.size(); i++) ref_views[i] = SeqView{ref.seqs[i].data(), (int64_t)ref.seqs[i].size()};
+
+    t0 = Clock::now();
+    std::cout << "\nFinding candidate bin locations for each read: " << std::endl;
+
+    auto run_shard = [&](Shard &sh) {
+        try {
+            const size_t nr = sh.last_read - sh.first_read;
+            std::ofstream fout("darwin." + std::to_string(sh.tid) + ".out");
+            if (!fout.is_open()) { sh.error = "ERROR cannot open output file"; return; }
+
+            // D-SOFT for every read of the shard, both strands (darwin.cpp:209-288)
+            auto td = Clock::now();
+            std::vector<std::vector<uint64_t>> cand_f(nr), cand_r(nr);
+            {
+                std::vector<std::thread> th;
+                std::atomic<size_t> next(0);
+                for (int t = 0; t < sh.dsoft_threads; t++) th.emplace_back([&] {
+                    SeedTable::Scratch scratch(*table, cfg.num_nz_bins);
+                    for (;;) {
+                        const size_t k = next.fetch_add(1);
+                        if (k >= nr) break;
+                        const size_t r = sh.first_read + k;
+                        table->dsoft(reads.seqs[r].data(), (uint32_t)reads.seqs[r].size(), cfg.num_seeds, cfg.threshold,
+                                     cfg.max_candidates, scratch, cand_f[k]);
+                        table->dsoft(rev_reads[r].data(), (uint32_t)rev_reads[r].size(), cfg.num_seeds, cfg.threshold,
+                                     cfg.max_candidates, scratch, cand_r[k]);
+                    }
+                });
+                for (auto &x : th) x.join();
+            }
+            // candidates -> calls, in the reference CPU build's order: per read forward then reverse
+            std::vector<GactCall> calls;
+            auto add_calls = [&](const std::vector<uint64_t> &cands, size_t read_id, bool comp) {
+                for (uint64_t c : cands) {
+                    int ref_pos = (int)(c >> 32);
+                    const int chr = bin_to_chr[(uint32_t)ref_pos / cfg.bin_size];
+                    ref_pos -= (int)(chr_start_bin[chr] * cfg.bin_size);
+                    const int query_pos = (int)(c & 0xffffffffu);
+                    if (ref_pos > (long long)ref.seqs[chr].size()) ref_pos = (int)ref.seqs[chr].size();   // darwin.cpp:222-224
+                    calls.push_back(GactCall{chr, (int32_t)read_id, ref_pos, query_pos, (uint8_t)(comp ? 1 : 0)});
+                }
+            };
+            for (size_t k = 0; k < nr; k++) {
+                sh.cand_fwd += cand_f[k].size();
+                sh.cand_rev += cand_r[k].size();
+                add_calls(cand_f[k], sh.first_read + k, false);
+                add_calls(cand_r[k], sh.first_read + k, true);
+            }
+            sh.dsoft_ms = ms_since(td);
+            {
+                std::lock_guard<std::mutex> lk(io_lock);
+                printf("num_candidates: %llu %llu\n", (unsigned long long)sh.cand_fwd, (unsigned long long)sh.cand_rev);
+                std::cout << "Time finding seeds: " << sh.dsoft_ms << " msec" << std::endl;
+            }
+
+            // engine for this shard's device; reads of the shard only
+            auto tg = Clock::now();
+            gact_params gp{cfg.match, cfg.mismatch, cfg.gap_open, cfg.gap_extend, cfg.tile_size, cfg.tile_overlap,
+                           cfg.first_tile_score_threshold};
+            const int max_tiles = (int)std::max<size_t>(1024, (calls.size() + 1) / 2 + 1);
+            gact_engine *eng = nullptr;
+            int rc = gact_engine_create(&eng, sh.device, &gp, std::min(max_tiles, 1 << 20), nullptr);
+            if (rc) { sh.error = std::string("gact_engine_create: ") + gact_last_error(nullptr); return; }
+            if (kernel_variant) gact_engine_set_kernel(eng, kernel_variant);
+            std::vector<const char *> ptrs;
+            std::vector<int64_t> lens;
+            auto upload = [&](int set, const std::vector<std::string> &v, size_t a, size_t b) {
+                ptrs.clear(); lens.clear();
+                for (size_t i = a; i < b; i++) { ptrs.push_back(v[i].data()); lens.push_back((int64_t)v[i].size()); }
+                int r2 = gact_engine_upload(eng, set, (int64_t)ptrs.size(), ptrs.data(), lens.data());
+                if (r2) throw std::runtime_error(std::string("gact_engine_upload: ") + gact_last_error(eng));
+            };
+            upload(GACT_SET_REF, ref.seqs, 0, ref.seqs.size());
+            upload(GACT_SET_READS, reads.seqs, sh.first_read, sh.last_read);
+            upload(GACT_SET_READS_RC, rev_reads, sh.first_read, sh.last_read);
+            std::vector<SeqView> rd(nr), rc_views(nr);
+            for (size_t k = 0; k < nr; k++) {
+                rd[k] = SeqView{reads.seqs[sh.first_read + k].data(), (int64_t)reads.seqs[sh.first_read + k].size()};
+                rc_views[k] = SeqView{rev_reads[sh.first_read + k].data(), (int64_t)rev_reads[sh.first_read + k].size()};
+            }
+            // query ids inside the engine are shard-local
+            for (auto &c : calls) c.query_id -= (int32_t)sh.first_read;
+            std::vector<GactAlignment> aln;
+            GactScheduler sched(eng, gp, ref_views, rd, rc_views, sh.dsoft_threads);
+            sched.run(calls, aln, &sh.stats);
+            gact_stats es;
+            gact_engine_stats(eng, &es);
+            sh.stats.device_ms = es.kernel_ms;
+            gact_engine_destroy(eng);
+
+            for (size_t k = 0; k < calls.size(); k++) {
+                const GactCall &c = calls[k];
+                const size_t read_id = sh.first_read + (size_t)c.query_id;
+                if (!(same_file && (size_t)c.ref_id == read_id) && aln[k].score > 0)        // gact.cpp:213
+                    fout << format_overlap(ref.names[c.ref_id], reads.names[read_id], aln[k], c.complement != 0);
+            }
+            fout.close();
+            sh.gact_ms = ms_since(tg);
+            {
+                std::lock_guard<std::mutex> lk(io_lock);
+                std::cout << "Time GACT calling: " << sh.gact_ms << " msec" << std::endl;
+            }
+        } catch (const std::exception &e) {
+            sh.error = e.what();
+        }
+    };
+
+    std::vector<std::thread> workers;
+    for (auto &sh : shards) workers.emplace_back(run_shard, std::ref(sh));
+    std::cout << workers.size() << " threads created\n";
+    std::cout << "Synchronizing all threads...\n";
+    for (auto &w : workers) w.join();
+    const long align_ms = ms_since(t0);
+    std::cout << "Time elapsed (seed table querying + aligning): " << align_ms << " msec" << std::endl;
+
+    int rcode = 0;
+    uint64_t tiles = 0, cells = 0;
+    double dev_ms = 0, sched_ms = 0;
+    for (auto &sh : shards) {
+        if (!sh.error.empty()) { fprintf(stderr, "shard %d: %s\n", sh.tid, sh.error.c_str()); rcode = 3; }
+        tiles += sh.stats.tiles; cells += sh.stats.cells;
+        dev_ms = std::max(dev_ms, sh.stats.device_ms);
+        sched_ms = std::max(sched_ms, sh.stats.wall_ms);
+    }
+    // machine-readable summary (one line; everything above mirrors the reference's prints)
+    printf("DARWIN_B200_SUMMARY {\"reads\": %zu, \"gpus\": %zu, \"tiles\": %llu, \"cells\": %llu, \"align_phase_ms\": %ld, "
+           "\"gact_sched_ms\": %.1f, \"gact_kernel_ms\": %.1f}\n",
+           num_reads, shards.size(), (unsigned long long)tiles, (unsigned long long)cells, align_ms, sched_ms, dev_ms);
+    delete table;
+    return rcode;
+}

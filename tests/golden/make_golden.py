@@ -112,7 +112,50 @@ def make_e2e_small():
     print("self lines:", len(lines))
 
 
+def make_dsoft_golden():
+    """Candidates of the reference's own SeedPosTable::DSOFT (seed_pos_table.cpp:100-167) for the
+    e2e_small reads (both strands) against the e2e_small reference."""
+    import ctypes as C
+    R = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libseed_ref.so"))
+    R.ref_seed_table_new.restype = C.c_void_p
+    R.ref_seed_table_new.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
+    R.ref_dsoft.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                            C.c_int, C.c_void_p, C.c_int]
+    out = os.path.join(HERE, "e2e_small")
+    refs = read_fasta_simple(os.path.join(out, "ref.fasta"))
+    reads = read_fasta_simple(os.path.join(out, "reads.fasta"))
+    refstr = b""
+    for _, s in refs:
+        refstr += s + (b"N" * ((64 - len(s) % 64) % 64))
+    t = R.ref_seed_table_new(refstr, len(refstr), 14, 32, 64, 4)
+    counts, cands = [], []
+    for _, s in reads:
+        for strand in (s, synth.revcomp(np.frombuffer(s, dtype=np.uint8)).tobytes()):
+            buf = np.zeros(4096, dtype=np.uint64)
+            n = R.ref_dsoft(t, strand, len(strand), len(refstr), 64, 800, 21, 1000000, 2500000, buf.ctypes.data, 4096)
+            counts.append(n)
+            cands.append(buf[:n].copy())
+    np.savez_compressed(os.path.join(HERE, "dsoft_e2e_small.npz"), counts=np.asarray(counts, dtype=np.int32),
+                        cands=np.concatenate(cands) if cands else np.zeros(0, dtype=np.uint64))
+    print("dsoft golden:", int(sum(counts)), "candidates over", len(counts), "strand calls")
+
+
+def read_fasta_simple(path):
+    recs, name, cur = [], None, []
+    for ln in open(path, "rb").read().split(b"\n"):
+        if ln.startswith(b">"):
+            if name is not None:
+                recs.append((name, b"".join(cur)))
+            name, cur = ln[1:].decode(), []
+        elif ln:
+            cur.append(ln)
+    if name is not None:
+        recs.append((name, b"".join(cur)))
+    return recs
+
+
 if __name__ == "__main__":
     O.build(ref=True)
     make_align_random()
     make_e2e_small()
+    make_dsoft_golden()

@@ -1,0 +1,83 @@
+"""GPU end-to-end parity: the drop-in `darwin` binary (C++ host + CUDA engine) against the
+sorted|uniq output of the reference CPU build (golden fixtures produced by tests/golden/make_golden.py
+with the unmodified reference, README:32 recipe)."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "e2e_small")
+EXE = os.path.join(ROOT, "darwin-gpu_b200", "darwin")
+
+PARAMS = """[GACT_scoring]
+match = {ma}
+mismatch = {mi}
+gap_open = {go}
+gap_extend = {ge}
+[DSOFT_params]
+seed_size = 14
+bin_size = 64
+window_size = 4
+threshold = 21
+num_seeds = 800
+seed_occurence_multiple = 32
+max_candidates = 1000000
+num_nz_bins = 2500000
+[GACT_first_tile]
+first_tile_size = 128
+first_tile_score_threshold = 35
+[GACT_extend]
+tile_size = {ts}
+tile_overlap = {to}
+"""
+
+
+def run_darwin(workdir, ref, reads, threads, cfg, env=None, extra=()):
+    os.makedirs(workdir, exist_ok=True)
+    with open(os.path.join(workdir, "params.cfg"), "w") as f:
+        f.write(PARAMS.format(**cfg))
+    for fn in os.listdir(workdir):
+        if fn.startswith("darwin.") and fn.endswith(".out"):
+            os.remove(os.path.join(workdir, fn))
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run([EXE, ref, reads, str(threads), *extra], cwd=workdir, capture_output=True, text=True, env=e, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    lines = []
+    for fn in sorted(os.listdir(workdir)):
+        if fn.startswith("darwin.") and fn.endswith(".out"):
+            lines += open(os.path.join(workdir, fn)).read().splitlines()
+    return sorted(set(lines)), r.stdout
+
+
+def expected(tag):
+    return open(os.path.join(GOLD, f"expected_{tag}.txt")).read().splitlines()
+
+
+CFGS = {"t320": dict(ma=1, mi=-1, go=-1, ge=-1, ts=320, to=120),
+        "t256": dict(ma=1, mi=-1, go=-1, ge=-1, ts=256, to=96),
+        "t512_s2": dict(ma=2, mi=-3, go=-5, ge=-2, ts=512, to=192)}
+
+
+@pytest.mark.parametrize("tag", sorted(CFGS))
+@pytest.mark.parametrize("kernel", ["0", "1"])
+def test_reads_vs_reference_matches_cpu_build(tmp_path, tag, kernel):
+    got, out = run_darwin(str(tmp_path), os.path.join(GOLD, "ref.fasta"), os.path.join(GOLD, "reads.fasta"), 4,
+                          CFGS[tag], env={"DARWIN_KERNEL": kernel})
+    assert got == expected(tag)
+    assert "num_candidates:" in out and "Time elapsed (seed table querying + aligning)" in out
+
+
+def test_self_alignment_same_file_suppression(tmp_path):
+    reads = os.path.join(GOLD, "reads.fasta")
+    got, _ = run_darwin(str(tmp_path), reads, reads, 3, CFGS["t320"], extra=("32", "64"))
+    assert got == expected("self_t320")
+
+
+def test_output_independent_of_thread_count(tmp_path):
+    a, _ = run_darwin(str(tmp_path / "a"), os.path.join(GOLD, "ref.fasta"), os.path.join(GOLD, "reads.fasta"), 1, CFGS["t320"])
+    b, _ = run_darwin(str(tmp_path / "b"), os.path.join(GOLD, "ref.fasta"), os.path.join(GOLD, "reads.fasta"), 7, CFGS["t320"])
+    assert a == b == expected("t320")
