@@ -78,6 +78,7 @@ void GactScheduler::run(const std::vector<GactCall> &calls, std::vector<GactAlig
     auto next_tile = [&](Active &a, bool adv_ok, gact_tile_desc &d) -> bool {
         const GactCall &c = calls[a.call];
         const int64_t RL = ref_of(c).len, QL = qry_of(c).len;
+        if (a.phase >= 2) return false;
         if (a.phase == 0) {
             if (a.ref_pos > 0 && a.query_pos > 0 && (adv_ok || a.first_tile)) {
                 a.t_ref_len = a.ref_pos > T ? T : a.ref_pos;
@@ -253,9 +254,16 @@ void GactScheduler::run(const std::vector<GactCall> &calls, std::vector<GactAlig
         return;
     }
 
+    // every round consumes at least one base of every live candidate, so the number of rounds is
+    // bounded by the longest sequence; anything beyond that is a logic error, not a long alignment
+    int64_t longest = 1;
+    for (const auto &v : refs_) longest = std::max(longest, v.len);
+    for (const auto &v : reads_) longest = std::max(longest, v.len);
+    const uint64_t round_cap = 4 * (uint64_t)longest + 64;
     bool live0 = build_and_submit(grp[0]);
     bool live1 = build_and_submit(grp[1]);
     while (live0 || live1) {
+        if (rounds > round_cap) throw std::runtime_error("GactScheduler: round limit exceeded (scheduler logic error)");
         if (live0) { wait_and_consume(grp[0]); }
         // group 1 (if any) is on the device while group 0 is consumed and resubmitted
         if (live0) live0 = build_and_submit(grp[0]);

@@ -44,7 +44,7 @@ def run_darwin(workdir, ref, reads, threads, cfg, env=None, extra=()):
             os.remove(os.path.join(workdir, fn))
     e = dict(os.environ)
     e.update(env or {})
-    r = subprocess.run([EXE, ref, reads, str(threads), *extra], cwd=workdir, capture_output=True, text=True, env=e, timeout=600)
+    r = subprocess.run([EXE, ref, reads, str(threads), *extra], cwd=workdir, capture_output=True, text=True, env=e, timeout=90)
     assert r.returncode == 0, r.stderr + r.stdout
     lines = []
     for fn in sorted(os.listdir(workdir)):
