@@ -225,7 +225,11 @@ int plan_launch(gact_engine *e)
     CU(e, cudaFuncSetAttribute((const void *)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_main));
     first_fn ff = pick_first_i32(C);
     CU(e, cudaFuncSetAttribute((const void *)ff, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * TS));
-    return s16_make_plan(e->params, e->num_sms, &e->s16) == 0
+    // experiment knobs (not part of the ABI): GACT_S16_WINDOW=smem|global, GACT_S16_WARPS=<per SM>
+    int mode = 0, wps = 0;
+    if (const char *m = getenv("GACT_S16_WINDOW")) mode = (strcmp(m, "global") == 0) ? 2 : (strcmp(m, "smem") == 0) ? 1 : 0;
+    if (const char *w = getenv("GACT_S16_WARPS")) wps = atoi(w);
+    return s16_make_plan(e->params, e->num_sms, mode, wps, &e->s16) == 0
                ? GACT_OK
                : fail(e, GACT_ERR_CUDA, "s16 kernel attribute setup failed");
 }
@@ -447,6 +451,7 @@ void gact_engine_destroy(gact_engine *e)
     for (int i = 0; i < GACT_MAX_SETS; i++) free_set(e->sets[i]);
     for (int k = 0; k < 2; k++) free_slot(e->slots[k]);
     if (e->d_gscratch) cudaFree(e->d_gscratch);
+    s16_free_plan(&e->s16);
     if (e->owns_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }

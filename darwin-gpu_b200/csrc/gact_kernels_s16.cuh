@@ -164,12 +164,16 @@ __device__ __forceinline__ uint32_t subst_score(uint32_t qc, uint32_t rlo, uint3
     return (eq & ma16) | (~eq & mi16);
 }
 
-template <int CS, bool LUT>
+// DIRG = false: the direction window lives in the warp's shared-memory carve-out;
+// DIRG = true : it lives in a per-warp scratch area in global memory that the warp rewrites for
+//               every tile (it stays L2-resident); shared memory then only holds the sequences,
+//               so occupancy is no longer bounded by the window size (needed for tile_size 1024).
+template <int CS, bool LUT, bool DIRG>
 __global__ void __launch_bounds__(256)
 gact_tile_s16_kernel(const __grid_constant__ KParams P, const gact_tile_desc *__restrict__ descs,
                      int n_tiles, const EffLen *__restrict__ eff,
                      gact_tile_result *__restrict__ results, uint32_t *__restrict__ states,
-                     int pitch_words, int *counter, size_t per_warp_bytes)
+                     int pitch_words, int *counter, size_t per_warp_bytes, uint8_t *gscratch, size_t dir_bytes)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     int lane;
@@ -185,7 +189,8 @@ gact_tile_s16_kernel(const __grid_constant__ KParams P, const gact_tile_desc *__
     uint32_t *rr = reinterpret_cast<uint32_t *>(my);
     uint16_t *qs = reinterpret_cast<uint16_t *>(my + (TS + 2) * 4);               // qs[j] = enc(Q[j])
     uint16_t *rb = reinterpret_cast<uint16_t *>(my + (TS + 2) * 6);               // rb[i] = enc(R[i])
-    void *dirbase = my + (((TS + 2) * 8 + 15) & ~15);
+    void *dirbase = DIRG ? (void *)(gscratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * dir_bytes)
+                         : (void *)(my + (((TS + 2) * 8 + 15) & ~15));
 
     // biased x16 domain: stored = 16*score + tag + B; B keeps every half-word that takes part in a
     // plain 32-bit add non-negative, so those adds can run as IMAD on the FMA pipe
@@ -357,6 +362,7 @@ gact_tile_s16_kernel(const __grid_constant__ KParams P, const gact_tile_desc *__
         }
         int corner = (__shfl_sync(FULL, corner16, c_lane) - B) >> 4;
         if (n == 0 || m == 0) corner = 0;
+        if (DIRG) __threadfence_block();
         __syncwarp();
         // rr[] (substitution tables) is dead now: reuse it as the per-state byte buffer (2*et <= 4*(TS+2))
         traceback_tile16<CS>(dw, rb, qs, reinterpret_cast<uint8_t *>(rr), lane, n, m, corner, P,
@@ -369,20 +375,40 @@ gact_tile_s16_kernel(const __grid_constant__ KParams P, const gact_tile_desc *__
 // ---------------------------------------------------------------------------
 // host-side planning / launch
 template <int CS>
-inline size_t s16_warp_bytes(int win_rows, int win_lanes)
+inline size_t s16_seq_bytes()
 {
     constexpr int TS = CS * 64;
-    return (size_t)(((TS + 2) * 8 + 15) & ~15) + DirWin16<CS>::bytes(win_rows, win_lanes);
+    return (size_t)(((TS + 2) * 8 + 15) & ~15);
+}
+inline size_t s16_seq_bytes(int CS)
+{
+    switch (CS) { case 4: return s16_seq_bytes<4>(); case 5: return s16_seq_bytes<5>(); case 8: return s16_seq_bytes<8>(); default: return s16_seq_bytes<16>(); }
+}
+inline size_t s16_dir_bytes(int CS, int rows, int lanes)
+{
+    switch (CS) {
+        case 4: return DirWin16<4>::bytes(rows, lanes);
+        case 5: return DirWin16<5>::bytes(rows, lanes);
+        case 8: return DirWin16<8>::bytes(rows, lanes);
+        default: return DirWin16<16>::bytes(rows, lanes);
+    }
 }
 
 typedef void (*s16_fn)(const KParams, const gact_tile_desc *, int, const EffLen *, gact_tile_result *,
-                       uint32_t *, int, int *, size_t);
-inline s16_fn s16_pick(int CS, bool lut)
+                       uint32_t *, int, int *, size_t, uint8_t *, size_t);
+template <int CS>
+inline s16_fn s16_pick_cs(bool lut, bool dirg)
+{
+    if (dirg) return lut ? gact_tile_s16_kernel<CS, true, true> : gact_tile_s16_kernel<CS, false, true>;
+    return lut ? gact_tile_s16_kernel<CS, true, false> : gact_tile_s16_kernel<CS, false, false>;
+}
+inline s16_fn s16_pick(int CS, bool lut, bool dirg)
 {
     switch (CS) {
-        case 4: return lut ? gact_tile_s16_kernel<4, true> : gact_tile_s16_kernel<4, false>;
-        case 5: return lut ? gact_tile_s16_kernel<5, true> : gact_tile_s16_kernel<5, false>;
-        case 8: return lut ? gact_tile_s16_kernel<8, true> : gact_tile_s16_kernel<8, false>;
+        case 4: return s16_pick_cs<4>(lut, dirg);
+        case 5: return s16_pick_cs<5>(lut, dirg);
+        case 8: return s16_pick_cs<8>(lut, dirg);
+        case 16: return s16_pick_cs<16>(lut, dirg);
         default: return nullptr;
     }
 }
@@ -392,11 +418,25 @@ struct S16Plan {
     bool ok = false;
     int CS = 0, win_rows = 0, win_lanes = 0, warps_per_cta = 0, ctas = 0, bias = 0;
     bool lut_ok = false;      // scores fit the one-PRMT substitution table
-    size_t per_warp_bytes = 0, smem = 0;
+    bool dirg = false;        // direction window in global (L2-resident) scratch instead of shared memory
+    size_t per_warp_bytes = 0, smem = 0, dir_bytes = 0;
+    uint8_t *d_scratch = nullptr;
 };
 
-inline int s16_make_plan(const gact_params &p, int num_sms, S16Plan *pl)
+inline void s16_free_plan(S16Plan *pl)
 {
+    if (pl->d_scratch) cudaFree(pl->d_scratch);
+    pl->d_scratch = nullptr;
+}
+
+// mode: 0 = default: global (L2-resident) scratch window -- measured 18 % faster than the
+//           shared-memory window at tile_size 320 because occupancy is no longer bounded by the
+//           22 KB window (24 instead of 9 warps per SM; profiles/r1_window_sweep.txt);
+//       1 = force shared memory (falls back to global when fewer than 4 warps per SM would fit);
+//       2 = force global scratch.  warps_per_sm: 0 = default (24).
+inline int s16_make_plan(const gact_params &p, int num_sms, int mode, int warps_per_sm, S16Plan *pl)
+{
+    s16_free_plan(pl);
     *pl = S16Plan();
     const int T = p.tile_size, et = p.tile_size - p.tile_overlap;
     // value range of the x16 tagged domain and the pseudo-row trick
@@ -407,37 +447,57 @@ inline int s16_make_plan(const gact_params &p, int num_sms, S16Plan *pl)
     if (hi > 30000 || p.mismatch > 0 || p.match < 0 || p.gap_open < -500 || p.gap_extend < -500 || p.mismatch < -1000)
         return 0;
     int CS;
-    if (T <= 256) CS = 4; else if (T <= 320) CS = 5; else if (T <= 512) CS = 8; else return 0;
+    if (T <= 256) CS = 4; else if (T <= 320) CS = 5; else if (T <= 512) CS = 8; else CS = 16;
     pl->CS = CS;
     pl->win_rows = (et + 1 < T) ? et + 1 : T;
     int wl = et / (2 * CS) + 2;
     pl->win_lanes = wl > 32 ? 32 : wl;
-    size_t pw = 0;
-    switch (CS) {
-        case 4: pw = s16_warp_bytes<4>(pl->win_rows, pl->win_lanes); break;
-        case 5: pw = s16_warp_bytes<5>(pl->win_rows, pl->win_lanes); break;
-        default: pw = s16_warp_bytes<8>(pl->win_rows, pl->win_lanes); break;
-    }
-    pw = (pw + 15) & ~(size_t)15;
-    pl->per_warp_bytes = pw;
+    const size_t seqb = s16_seq_bytes(CS);
+    pl->dir_bytes = s16_dir_bytes(CS, pl->win_rows, pl->win_lanes);
     const size_t SM = 228 * 1024, CTA_MAX = 227 * 1024;
-    int best_w = 0, best_c = 0, best_total = 0;
-    for (int w = 1; w <= 8; w++) {
-        const size_t cta = (size_t)w * pw;
-        if (cta > CTA_MAX) break;
-        int c = (int)(SM / (cta + 1024));
-        if (c > 16) c = 16;
-        if (c * w > 48) c = 48 / w;
-        if (c < 1) continue;
-        if (c * w > best_total || (c * w == best_total && w > best_w)) { best_total = c * w; best_w = w; best_c = c; }
-    }
-    if (best_total < 4) return 0;              // window too large for shared memory: int32/L2-scratch kernel instead
-    pl->warps_per_cta = best_w;
-    pl->ctas = best_c * num_sms;
-    pl->smem = (size_t)best_w * pw;
-    if (cudaFuncSetAttribute((const void *)s16_pick(CS, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem) != cudaSuccess ||
-        cudaFuncSetAttribute((const void *)s16_pick(CS, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem) != cudaSuccess)
-        return -1;
+
+    auto plan_smem = [&]() -> bool {
+        const size_t pw = (seqb + pl->dir_bytes + 15) & ~(size_t)15;
+        int best_w = 0, best_c = 0, best_total = 0;
+        for (int w = 1; w <= 8; w++) {
+            const size_t cta = (size_t)w * pw;
+            if (cta > CTA_MAX) break;
+            int c = (int)(SM / (cta + 1024));
+            if (c > 16) c = 16;
+            if (c * w > 48) c = 48 / w;
+            if (c < 1) continue;
+            if (c * w > best_total || (c * w == best_total && w > best_w)) { best_total = c * w; best_w = w; best_c = c; }
+        }
+        if (best_total < 4) return false;
+        pl->dirg = false;
+        pl->per_warp_bytes = pw;
+        pl->warps_per_cta = best_w;
+        pl->ctas = best_c * num_sms;
+        pl->smem = (size_t)best_w * pw;
+        return true;
+    };
+    auto plan_global = [&]() -> bool {
+        int wps = warps_per_sm > 0 ? warps_per_sm : 24;
+        if (wps > 32) wps = 32;
+        const int w = 4;                                   // warps per CTA
+        const int c = (wps + w - 1) / w;
+        pl->dirg = true;
+        pl->per_warp_bytes = seqb;
+        pl->warps_per_cta = w;
+        pl->ctas = c * num_sms;
+        pl->smem = (size_t)w * seqb;
+        const size_t total = (size_t)pl->ctas * w * pl->dir_bytes;
+        if (cudaMalloc(&pl->d_scratch, total) != cudaSuccess) { cudaGetLastError(); pl->d_scratch = nullptr; return false; }
+        return true;
+    };
+    bool ok = false;
+    if (mode == 1) ok = plan_smem() || plan_global();
+    else ok = plan_global() || plan_smem();
+    if (!ok) return 0;
+    for (int lut = 0; lut < 2; lut++)
+        if (cudaFuncSetAttribute((const void *)s16_pick(CS, lut != 0, pl->dirg), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)pl->smem) != cudaSuccess)
+            return -1;
     pl->ok = true;
     return 0;
 }
@@ -455,8 +515,9 @@ inline void s16_launch(const S16Plan &pl, KParams kp, const gact_tile_desc *desc
     int ctas = pl.ctas;
     const int need = (n + pl.warps_per_cta - 1) / pl.warps_per_cta;
     if (need < ctas) ctas = need;
-    s16_pick(pl.CS, lut)<<<ctas, pl.warps_per_cta * 32, pl.smem, st>>>(kp, descs, n, eff, results, states, pitch_words,
-                                                                  counter, pl.per_warp_bytes);
+    s16_pick(pl.CS, lut, pl.dirg)<<<ctas, pl.warps_per_cta * 32, pl.smem, st>>>(kp, descs, n, eff, results, states,
+                                                                              pitch_words, counter, pl.per_warp_bytes,
+                                                                              pl.d_scratch, pl.dir_bytes);
 }
 
 }  // namespace gact
