@@ -81,3 +81,23 @@ def test_output_independent_of_thread_count(tmp_path):
     a, _ = run_darwin(str(tmp_path / "a"), os.path.join(GOLD, "ref.fasta"), os.path.join(GOLD, "reads.fasta"), 1, CFGS["t320"])
     b, _ = run_darwin(str(tmp_path / "b"), os.path.join(GOLD, "ref.fasta"), os.path.join(GOLD, "reads.fasta"), 7, CFGS["t320"])
     assert a == b == expected("t320")
+
+
+def test_reference_gpu_host_code_links_against_library(tmp_path):
+    """INTEGRATION.md route B: the reference's own darwin.cpp + gact.cpp (-D GPU), built in place and
+    linked to libgact_b200.so through host/legacy_adapter.cpp, reproduces the CPU build's output.
+    One host thread: the reference's GPU-build base conversion races with more."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "darwin_gpu_adapter")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/darwin_gpu_adapter not built (needs /root/reference at build time)")
+    wd = str(tmp_path)
+    with open(os.path.join(wd, "params.cfg"), "w") as f:
+        f.write(PARAMS.format(**CFGS["t320"]))
+    r = subprocess.run([exe, os.path.join(GOLD, "ref.fasta"), os.path.join(GOLD, "reads.fasta"), "1", "8", "64"],
+                       cwd=wd, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = []
+    for fn in sorted(os.listdir(wd)):
+        if fn.startswith("darwin.") and fn.endswith(".out"):
+            lines += open(os.path.join(wd, fn)).read().splitlines()
+    assert sorted(set(lines)) == expected("t320")
