@@ -181,6 +181,26 @@ def reference_main(args):
     print(json.dumps(line))
 
 
+def shard_range(n_items, world, rank):
+    """Contiguous shard of `n_items` for `rank` -- the reference's rule ceil(N / threads) per worker
+    (darwin.cpp:620-623), also used by host/darwin_main.cpp for its per-GPU read ranges."""
+    per = -(-n_items // max(world, 1))
+    lo = min(n_items, per * rank)
+    return lo, min(n_items, lo + per)
+
+
+def reduce_over_ranks(dist, maxima, sums, device):
+    """MAX-reduce the per-rank timings and SUM-reduce the per-rank work; identity for one rank.
+    Works with NCCL (device tensors) and gloo (CPU tensors, used by the CPU tests)."""
+    import torch
+    t = torch.tensor(list(maxima), dtype=torch.float64, device=device)
+    c = torch.tensor(list(sums), dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    return t.tolist(), c.tolist()
+
+
 # ---------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -277,13 +297,8 @@ def main():
     d2h = n * (24 + pitch * 4)
 
     # ---- reductions over ranks ---------------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
-    c = torch.tensor([float(cells)], dtype=torch.float64, device=f"cuda:{local}")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_ms_max = t.tolist()
-    total_cells = c.item()
+    (dev_ms_max, e2e_ms_max), (total_cells,) = reduce_over_ranks(dist, [dev_ms, e2e_s * 1e3], [float(cells)],
+                                                                 f"cuda:{local}")
 
     if rank == 0:
         gcups = total_cells * args.steps / (dev_ms_max * 1e-3) / 1e9
