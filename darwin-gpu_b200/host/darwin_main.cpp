@@ -54,6 +54,7 @@ struct Shard {
     long dsoft_ms = 0, gact_ms = 0;
     uint64_t cand_fwd = 0, cand_rev = 0;
     std::string error;
+    gact_engine *eng = nullptr;               // created before the align phase (like GPU_init, darwin.cpp:611)
 };
 
 int main(int argc, char **argv)
@@ -126,6 +127,45 @@ int main(int argc, char **argv)
     std::cout << "Number of reads: " << num_reads << std::endl;
     std::cout << "Time elapsed (loading reads): " << ms_since(t0) << " msec" << std::endl;
 
+    // ---- shards: contiguous read ranges, one per GPU (darwin.cpp:619-629 rule) ----------------
+    const int G = (int)std::max<size_t>(1, std::min<size_t>((size_t)want_gpus, std::max<size_t>(num_reads, 1)));
+    const size_t per = (num_reads + G - 1) / std::max(G, 1);
+    std::vector<Shard> shards;
+    for (int g = 0; g < G; g++) {
+        Shard s;
+        s.tid = g; s.device = g;
+        s.first_read = std::min(num_reads, per * g);
+        s.last_read = std::min(num_reads, per * (g + 1));
+        s.dsoft_threads = std::max(1, num_threads / G);
+        if (s.first_read < s.last_read || g == 0) shards.push_back(s);
+    }
+
+    // ---- engines: one per shard/GPU, created and loaded while the seed table is being built -------
+    const gact_params gp{cfg.match, cfg.mismatch, cfg.gap_open, cfg.gap_extend, cfg.tile_size, cfg.tile_overlap,
+                         cfg.first_tile_score_threshold};
+    auto t_gpu = Clock::now();
+    std::vector<std::thread> init_threads;
+    for (auto &sh : shards) {
+        Shard *shp = &sh;
+        init_threads.emplace_back([&, shp] {
+            Shard &S = *shp;
+            int rc = gact_engine_create(&S.eng, S.device, &gp, 1 << 17, nullptr);
+            if (rc) { S.error = std::string("gact_engine_create: ") + gact_last_error(nullptr); return; }
+            if (kernel_variant) gact_engine_set_kernel(S.eng, kernel_variant);
+            std::vector<const char *> ptrs;
+            std::vector<int64_t> lens;
+            auto upload = [&](int set, const std::vector<std::string> &v, size_t a, size_t b) {
+                ptrs.clear(); lens.clear();
+                for (size_t i = a; i < b; i++) { ptrs.push_back(v[i].data()); lens.push_back((int64_t)v[i].size()); }
+                if (gact_engine_upload(S.eng, set, (int64_t)ptrs.size(), ptrs.data(), lens.data()) && S.error.empty())
+                    S.error = std::string("gact_engine_upload: ") + gact_last_error(S.eng);
+            };
+            upload(GACT_SET_REF, ref.seqs, 0, ref.seqs.size());
+            upload(GACT_SET_READS, reads.seqs, S.first_read, S.last_read);
+            upload(GACT_SET_READS_RC, rev_reads, S.first_read, S.last_read);
+        });
+    }
+
     // ---- seed table -----------------------------------------------------------------------
     std::cout << "\nConstructing seed position table ...\n";
     t0 = Clock::now();
@@ -139,18 +179,10 @@ int main(int argc, char **argv)
     }
     std::cout << "Time elapsed (seed position table construction): " << ms_since(t0) << " msec" << std::endl;
 
-    // ---- shards: contiguous read ranges, one per GPU (darwin.cpp:619-629 rule) ----------------
-    const int G = (int)std::max<size_t>(1, std::min<size_t>((size_t)want_gpus, std::max<size_t>(num_reads, 1)));
-    const size_t per = (num_reads + G - 1) / std::max(G, 1);
-    std::vector<Shard> shards;
-    for (int g = 0; g < G; g++) {
-        Shard s;
-        s.tid = g; s.device = g;
-        s.first_read = std::min(num_reads, per * g);
-        s.last_read = std::min(num_reads, per * (g + 1));
-        s.dsoft_threads = std::max(1, num_threads / G);
-        if (s.first_read < s.last_read || g == 0) shards.push_back(s);
-    }
+    for (auto &th : init_threads) th.join();
+    std::cout << "Time elapsed (GPU init, overlapped with the seed table): " << ms_since(t_gpu) << " msec" << std::endl;
+    for (auto &sh : shards)
+        if (!sh.error.empty()) { fprintf(stderr, "shard %d: %s\n", sh.tid, sh.error.c_str()); return 3; }
 
     std::vector<SeqView> ref_views(ref.seqs.size());
     for (size_t i = 0; i < ref.seqs.size(); i++) ref_views[i] = SeqView{ref.seqs[i].data(), (int64_t)ref.seqs[i].size()};
@@ -209,26 +241,8 @@ int main(int argc, char **argv)
                 std::cout << "Time finding seeds: " << sh.dsoft_ms << " msec" << std::endl;
             }
 
-            // engine for this shard's device; reads of the shard only
             auto tg = Clock::now();
-            gact_params gp{cfg.match, cfg.mismatch, cfg.gap_open, cfg.gap_extend, cfg.tile_size, cfg.tile_overlap,
-                           cfg.first_tile_score_threshold};
-            const int max_tiles = (int)std::max<size_t>(1024, (calls.size() + 1) / 2 + 1);
-            gact_engine *eng = nullptr;
-            int rc = gact_engine_create(&eng, sh.device, &gp, std::min(max_tiles, 1 << 20), nullptr);
-            if (rc) { sh.error = std::string("gact_engine_create: ") + gact_last_error(nullptr); return; }
-            if (kernel_variant) gact_engine_set_kernel(eng, kernel_variant);
-            std::vector<const char *> ptrs;
-            std::vector<int64_t> lens;
-            auto upload = [&](int set, const std::vector<std::string> &v, size_t a, size_t b) {
-                ptrs.clear(); lens.clear();
-                for (size_t i = a; i < b; i++) { ptrs.push_back(v[i].data()); lens.push_back((int64_t)v[i].size()); }
-                int r2 = gact_engine_upload(eng, set, (int64_t)ptrs.size(), ptrs.data(), lens.data());
-                if (r2) throw std::runtime_error(std::string("gact_engine_upload: ") + gact_last_error(eng));
-            };
-            upload(GACT_SET_REF, ref.seqs, 0, ref.seqs.size());
-            upload(GACT_SET_READS, reads.seqs, sh.first_read, sh.last_read);
-            upload(GACT_SET_READS_RC, rev_reads, sh.first_read, sh.last_read);
+            gact_engine *eng = sh.eng;
             std::vector<SeqView> rd(nr), rc_views(nr);
             for (size_t k = 0; k < nr; k++) {
                 rd[k] = SeqView{reads.seqs[sh.first_read + k].data(), (int64_t)reads.seqs[sh.first_read + k].size()};
@@ -243,6 +257,7 @@ int main(int argc, char **argv)
             gact_engine_stats(eng, &es);
             sh.stats.device_ms = es.kernel_ms;
             gact_engine_destroy(eng);
+            sh.eng = nullptr;
 
             for (size_t k = 0; k < calls.size(); k++) {
                 const GactCall &c = calls[k];
