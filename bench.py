@@ -293,7 +293,7 @@ def main():
     res_e2e = np.concatenate([o[0] for o in out])
     assert (res_e2e == res_dev).all(), "e2e and device-resident legs disagree"
     pitch = eng.pitch
-    h2d = n * 32 + int(mb["first"].sum()) * 4
+    h2d = n * 36 + int(mb["first"].sum()) * 4
     d2h = n * (24 + pitch * 4)
 
     # ---- reductions over ranks ---------------------------------------------------------------

@@ -15,6 +15,7 @@
 #include "gact_common.cuh"
 #include "gact_kernels_i32.cuh"
 #include "gact_kernels_s16.cuh"
+#include "gact_kernels_s16h.cuh"
 
 using namespace gact;
 
@@ -36,6 +37,7 @@ struct Slot {
     uint32_t *d_states = nullptr, *h_states = nullptr;
     EffLen *d_eff = nullptr;
     int *d_first = nullptr, *h_first = nullptr;
+    int *d_order = nullptr, *h_order = nullptr;      // tiles by descending reference length (pairs similar tiles)
     int *d_counters = nullptr;            // [0] first pass, [1] main pass
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
     int n = 0, n_first = 0;
@@ -62,6 +64,7 @@ struct gact_engine {
     size_t smem_main = 0;
     uint8_t *d_gscratch = nullptr;
     S16Plan s16;              // packed s16x2 kernel launch plan (s16.ok: usable for these params)
+    S16HPlan s16h;            // two-tiles-per-warp mapping of the same kernel (tile_size <= 320)
     SeqSetHost sets[GACT_MAX_SETS];
     Slot slots[2];
     int head = 0, tail = 0, inflight = 0;   // async ring
@@ -131,6 +134,8 @@ void free_slot(Slot &s)
     if (s.d_states) cudaFree(s.d_states);
     if (s.d_eff) cudaFree(s.d_eff);
     if (s.d_first) cudaFree(s.d_first);
+    if (s.d_order) cudaFree(s.d_order);
+    if (s.h_order) cudaFreeHost(s.h_order);
     if (s.d_counters) cudaFree(s.d_counters);
     if (s.h_descs) cudaFreeHost(s.h_descs);
     if (s.h_results) cudaFreeHost(s.h_results);
@@ -229,6 +234,12 @@ int plan_launch(gact_engine *e)
     int mode = 0, wps = 0;
     if (const char *m = getenv("GACT_S16_WINDOW")) mode = (strcmp(m, "global") == 0) ? 2 : (strcmp(m, "smem") == 0) ? 1 : 0;
     if (const char *w = getenv("GACT_S16_WARPS")) wps = atoi(w);
+    // GACT_S16_HALF=0 disables the two-tiles-per-warp mapping
+    const char *hv = getenv("GACT_S16_HALF");
+    if (!(hv && atoi(hv) == 0) && mode != 1) {
+        if (s16h_make_plan(e->params, e->num_sms, wps, &e->s16h) != 0)
+            return fail(e, GACT_ERR_CUDA, "s16h kernel attribute setup failed");
+    }
     return s16_make_plan(e->params, e->num_sms, mode, wps, &e->s16) == 0
                ? GACT_OK
                : fail(e, GACT_ERR_CUDA, "s16 kernel attribute setup failed");
@@ -254,7 +265,10 @@ int launch_batch(gact_engine *e, Slot &s)
         ff<<<ctas, 256, 8 * TS, st>>>(e->kp, s.d_descs, s.d_first, s.n_first, s.d_eff, s.d_counters + 0);
         e->stats.kernel_launches++;
     }
-    if (use_s16(e)) {
+    if (use_s16(e) && e->s16h.ok) {
+        s16h_launch(e->s16h, e->kp, s.d_descs, s.d_order, s.n, s.d_eff, s.d_results, s.d_states, e->pitch_words,
+                    s.d_counters + 1, st);
+    } else if (use_s16(e)) {
         s16_launch(e->s16, e->kp, s.d_descs, s.n, s.d_eff, s.d_results, s.d_states, e->pitch_words,
                    s.d_counters + 1, st);
     } else {
@@ -288,6 +302,12 @@ int check_descs(gact_engine *e, int n, const gact_tile_desc *descs, Slot &s)
     }
     s.n_first = nf;
     s.cells = cells;
+    // counting sort by reference length, longest first: the two tiles a warp aligns side by side
+    // then have the same number of wavefront steps, and the long tiles start first
+    std::vector<int> start((size_t)T + 2, 0);
+    for (int t = 0; t < n; t++) start[(size_t)(T - descs[t].ref_len) + 1]++;
+    for (int k = 1; k <= T + 1; k++) start[k] += start[k - 1];
+    for (int t = 0; t < n; t++) s.h_order[start[(size_t)(T - descs[t].ref_len)]++] = t;
     return GACT_OK;
 }
 
@@ -302,7 +322,8 @@ int enqueue(gact_engine *e, Slot &s, int n, const gact_tile_desc *descs)
     CU(e, cudaMemcpyAsync(s.d_descs, s.h_descs, (size_t)n * sizeof(gact_tile_desc), cudaMemcpyHostToDevice, e->stream));
     if (s.n_first)
         CU(e, cudaMemcpyAsync(s.d_first, s.h_first, (size_t)s.n_first * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    e->stats.h2d_bytes += (double)n * sizeof(gact_tile_desc) + (double)s.n_first * sizeof(int);
+    CU(e, cudaMemcpyAsync(s.d_order, s.h_order, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    e->stats.h2d_bytes += (double)n * (sizeof(gact_tile_desc) + sizeof(int)) + (double)s.n_first * sizeof(int);
     return GACT_OK;
 }
 
@@ -425,6 +446,8 @@ int gact_engine_create(gact_engine **out, int device, const gact_params *p, int 
             CK(cudaMalloc(&s.d_states, n * e->pitch_words * 4));
             CK(cudaMalloc(&s.d_eff, n * sizeof(EffLen)));
             CK(cudaMalloc(&s.d_first, n * sizeof(int)));
+            CK(cudaMalloc(&s.d_order, n * sizeof(int)));
+            CK(cudaMallocHost(&s.h_order, n * sizeof(int)));
             CK(cudaMalloc(&s.d_counters, 2 * sizeof(int)));
             CK(cudaMallocHost(&s.h_descs, n * sizeof(gact_tile_desc)));
             CK(cudaMallocHost(&s.h_results, n * sizeof(gact_tile_result)));
@@ -452,6 +475,7 @@ void gact_engine_destroy(gact_engine *e)
     for (int k = 0; k < 2; k++) free_slot(e->slots[k]);
     if (e->d_gscratch) cudaFree(e->d_gscratch);
     s16_free_plan(&e->s16);
+    s16h_free_plan(&e->s16h);
     if (e->owns_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }

@@ -1,0 +1,408 @@
+// gact_kernels_s16h.cuh -- packed s16x2 DPX GACT tile kernel, LANES lanes per tile.
+//
+// Same arithmetic as gact_kernels_s16.cuh (tagged x16 domain, see there), different mapping:
+// a tile is owned by a SEGMENT of LANES = 16 lanes, so a warp aligns 32 / LANES = 2 tiles at a
+// time and each lane owns two strips of CS = tile_size / (2 * LANES) columns (10 at T = 320).
+// Compared with one tile per warp this halves the wavefront skew (n + 31 instead of n + 63 steps)
+// and spreads the per-step overhead (edge shuffle, predicates, row fetch) over twice as many
+// cells.  The direction window lives in per-segment global scratch (L2-resident).
+#pragma once
+#include "gact_kernels_s16.cuh"
+
+namespace gact {
+
+template <int CS>
+struct DirWinH {
+    static constexpr int NW = CS / 4;                 // 32-bit words per lane-step (4 columns x 2 strips each)
+    static constexpr int R = CS % 4;                  // leftover columns, kept in one 16-bit field (R <= 2)
+    static_assert(R <= 2, "unsupported strip width");
+    int i0, lane0, nl;
+    uint32_t *w;
+    uint16_t *h;
+    __device__ __forceinline__ void init(void *base, int n, int m, const KParams &P)
+    {
+        i0 = max(n - P.et, 1);
+        const int j0 = max(m - P.et, 1);
+        lane0 = ((j0 - 1) / CS) >> 1;
+        nl = P.win_lanes;
+        w = reinterpret_cast<uint32_t *>(base);
+        h = reinterpret_cast<uint16_t *>(w + (size_t)(P.win_rows + 1) * nl * NW);
+    }
+    // 4-bit code of cell (i, j): bits 3:2 = M/I/D tag, bit 1 = ins flag, bit 0 = del flag
+    __device__ __forceinline__ int load(int i, int j) const
+    {
+        const int s = (j - 1) / CS, c = (j - 1) - s * CS;
+        const int lane = s >> 1, half = s & 1;
+        const int e = (i + half - i0) * nl + (lane - lane0);
+        if (c < NW * 4) return (w[e * NW + (c >> 2)] >> (16 * half + 4 * (3 - (c & 3)))) & 15;
+        return (h[e] >> (8 * half + 4 * (R - 1 - (c - NW * 4)))) & 15;
+    }
+    static __host__ __device__ size_t bytes(int win_rows, int win_lanes)
+    {
+        size_t s = (size_t)(win_rows + 1) * win_lanes * (NW * 4 + (R ? 2 : 0));
+        return (s + 15) & ~(size_t)15;
+    }
+};
+
+template <int CS, int LANES, bool LUT>
+__global__ void __launch_bounds__(128, 4)
+gact_tile_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *__restrict__ descs,
+                      const int *__restrict__ order, int n_tiles, const EffLen *__restrict__ eff,
+                      gact_tile_result *__restrict__ results, uint32_t *__restrict__ states,
+                      int pitch_words, int *counter, size_t seq_bytes, uint8_t *gscratch, size_t dir_bytes)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int TPW = 32 / LANES;                   // tiles per warp
+    constexpr int TS = CS * 2 * LANES;
+    constexpr int NW = DirWinH<CS>::NW;
+    constexpr int R = DirWinH<CS>::R;
+    constexpr unsigned SEGMASK = (LANES == 32) ? 0xffffffffu : ((1u << LANES) - 1u);
+    int lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    const int warp = threadIdx.x >> 5;
+    const int seg = lane / LANES, sl = lane % LANES;
+    const int segbase = seg * LANES;
+
+    // per-segment carve-out: rr[TS+2] words | qs[TS+2] halves | rb[TS+2] halves
+    uint8_t *my = smem + ((size_t)warp * TPW + seg) * seq_bytes;
+    uint32_t *rr = reinterpret_cast<uint32_t *>(my);
+    uint16_t *qs = reinterpret_cast<uint16_t *>(my + (TS + 2) * 4);
+    uint16_t *rb = reinterpret_cast<uint16_t *>(my + (TS + 2) * 6);
+    void *dirbase = gscratch + (((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * TPW + seg) * dir_bytes;
+
+    const int B = P.s16_bias;
+    const uint32_t Bp = pk16(B);
+    const uint32_t ma16 = pk16(P.match * 16), mi16 = pk16(P.mismatch * 16);
+    const uint32_t ge16 = pk16(P.gap_extend * 16);
+    const int KO = (P.gap_open * 16) * 65537;
+    const int KI = (P.gap_open * 16 - 5) * 65537;
+    const int KD = (P.gap_open * 16 - 10) * 65537;
+    const int ONE = P.one;
+    const uint32_t borderD_tag = ((uint32_t)(B + P.gap_open * 16 + 5) << 16) | (uint32_t)B;
+    const uint32_t borderD_raw = ((uint32_t)(B + P.gap_open * 16) << 16) | (uint32_t)B;
+    const uint32_t lut_mis = (uint32_t)((P.mismatch * 16) & 0xff) * 0x01010101u;
+    const int et = P.et;
+
+    for (;;) {
+        int t0 = 0;
+        if (lane == 0) t0 = atomicAdd(counter, TPW);
+        t0 = __shfl_sync(FULL, t0, 0);
+        if (t0 >= n_tiles) break;
+        const bool valid = (t0 + seg) < n_tiles;
+        const int t = valid ? (order ? order[t0 + seg] : t0 + seg) : 0;
+
+        gact_tile_desc d;
+        d.ref_off = 0; d.query_off = 0; d.ref_len = 0; d.query_len = 0; d.ref_set = 0; d.query_set = 0; d.reverse = 0; d.first = 0;
+        if (valid) d = descs[t];
+        int n = d.ref_len, m = d.query_len;
+        if (valid && d.first) { n = eff[t].n; m = eff[t].m; }
+        const SeqSetDev &rset = P.sets[d.ref_set];
+        const SeqSetDev &qset = P.sets[d.query_set];
+
+        __syncwarp();
+        if (n > 0 && m > 0) {
+            for (int x = sl; x <= n + 1; x += LANES) {
+                const bool in = (x >= 1 && x <= n);
+                const int base = in ? tile_base(rset, d.ref_off, d.ref_len, d.reverse, x) : 0;
+                rb[x] = (uint16_t)(in ? enc_base(base) : SENT_R);
+                if (LUT) {
+                    const int code = (base == 'A') ? 0 : (base == 'C') ? 1 : (base == 'G') ? 2 : (base == 'T') ? 3 : 4;
+                    uint32_t w = lut_mis;
+                    if (in && code < 4) w ^= (uint32_t)(((P.match ^ P.mismatch) * 16) & 0xff) << (8 * code);
+                    rr[x] = w;
+                }
+            }
+            for (int x = sl; x <= m; x += LANES)
+                qs[x] = (x >= 1) ? (uint16_t)enc_base(tile_base(qset, d.query_off, d.query_len, d.reverse, x)) : (uint16_t)SENT_Q;
+        }
+        __syncwarp();
+        if (!LUT && n > 0 && m > 0) {
+            for (int x = sl; x <= n + 1; x += LANES)
+                rr[x] = (uint32_t)rb[x] | ((uint32_t)(x >= 1 ? rb[x - 1] : (uint16_t)SENT_R) << 16);
+        }
+        __syncwarp();
+
+        uint32_t q[CS];
+#pragma unroll
+        for (int c = 0; c < CS; c++) {
+            const int jl = (2 * sl) * CS + c + 1, jh = (2 * sl + 1) * CS + c + 1;
+            const uint32_t el = jl <= m ? (uint32_t)qs[jl] : SENT_Q + c, eh = jh <= m ? (uint32_t)qs[jh] : SENT_Q + c;
+            if (LUT) {
+                const uint32_t tl = (el >> 1) & 3u, th = (eh >> 1) & 3u;       // A0 C1 G3 T2 -> 0 1 2 3 below
+                const uint32_t l2 = (jl <= m) ? (tl ^ (tl >> 1)) : 0u, h2 = (jh <= m) ? (th ^ (th >> 1)) : 0u;
+                q[c] = l2 | ((8u | l2) << 4) | ((4u | h2) << 8) | ((12u | h2) << 12);
+            } else {
+                q[c] = el | (eh << 16);
+            }
+        }
+
+        DirWinH<CS> dw;
+        dw.init(dirbase, n, m, P);
+        const int laststrip = (m > 0) ? (m - 1) / CS : -1;
+        const int lastlane = laststrip >> 1;                       // segment-local
+        const int c_lane = max(lastlane, 0), c_half = laststrip & 1, c_col = (m > 0) ? (m - 1) - laststrip * CS : 0;
+        const int kc = n + 2 * c_lane + c_half;
+        const bool work = (n > 0 && m > 0);
+        const int steps_seg = work ? n + 1 + 2 * lastlane : 0;
+        int steps = steps_seg, k1 = work ? min(dw.i0 - 1, steps_seg) : 0x3fffffff;
+#pragma unroll
+        for (int o = LANES; o < 32; o <<= 1) {
+            steps = max(steps, __shfl_xor_sync(FULL, steps, o));
+            k1 = min(k1, __shfl_xor_sync(FULL, k1, o));
+        }
+        k1 = min(k1, steps);
+        const int kfirst = (work && sl <= lastlane) ? 2 * sl + 1 : 0x3fffffff;
+        const int kstore = (work && sl >= dw.lane0) ? dw.i0 + 2 * sl : 0x3fffffff;
+        const uint32_t *rrp = rr - 2 * sl;               // rrp[k] = rr[k - 2*sl]
+
+        // ---------------- phase 1: rows above every segment's window, score only ----------------
+        uint32_t Gup[CS], IoUp[CS], IcUp[CS];
+#pragma unroll
+        for (int c = 0; c < CS; c++) {
+            Gup[c] = Bp;
+            IoUp[c] = pk16(B + P.gap_open * 16, S16_NEG);
+            IcUp[c] = pk16(S16_NEG, S16_NEG);
+        }
+        uint32_t eG = Bp, eD = pk16(S16_NEG), diag = Bp;
+        int k = 1;
+        for (; k <= k1; k++) {
+            const uint32_t pack = __byte_perm(eG, eD, 0x7632);
+            uint32_t recv = __shfl_up_sync(FULL, pack, 1, LANES);
+            if (sl == 0) recv = borderD_raw;
+            const uint32_t inG = __byte_perm(recv, eG, 0x5410);
+            const uint32_t inD = __byte_perm(recv, eD, 0x5432);
+            if ((unsigned)(k - kfirst) <= (unsigned)n) {
+                const uint32_t rlo = rrp[k], rhi = LUT ? rrp[k - 1] : 0u;
+                uint32_t hd = diag, dv = inD;
+#pragma unroll
+                for (int c = 0; c < CS; c++) {
+                    const uint32_t sc = subst_score<LUT>(q[c], rlo, rhi, ma16, mi16);
+                    const uint32_t mc = __viaddmax_s16x2(hd, sc, Bp);
+                    hd = Gup[c];
+                    const uint32_t iv = __viaddmax_s16x2(IcUp[c], ge16, IoUp[c]);
+                    Gup[c] = __vimax3_s16x2(mc, iv, dv);
+                    const uint32_t mo = (uint32_t)((int)mc * ONE + KO);
+                    IoUp[c] = mo;
+                    IcUp[c] = iv;
+                    dv = __viaddmax_s16x2(dv, ge16, mo);
+                }
+                eG = Gup[CS - 1];
+                eD = dv;
+                diag = inG;
+            }
+        }
+        // ---------------- switch to the tagged domain ----------------
+#pragma unroll
+        for (int c = 0; c < CS; c++) {
+            IoUp[c] = __vadd2(IoUp[c], pk16(10));
+            IcUp[c] = __vadd2(IcUp[c], pk16(8));
+        }
+        eD = __vadd2(eD, pk16(4));
+
+        // ---------------- phase 2: window rows, tagged values + direction codes ----------------
+        uint32_t *wptr = dw.w + ((k - 2 * sl - dw.i0) * dw.nl + (sl - dw.lane0)) * NW;
+        uint16_t *hptr = dw.h + ((k - 2 * sl - dw.i0) * dw.nl + (sl - dw.lane0));
+        int corner16 = B;
+        for (; k <= steps; k++) {
+            const uint32_t pack = __byte_perm(eG, eD, 0x7632);
+            uint32_t recv = __shfl_up_sync(FULL, pack, 1, LANES);
+            if (sl == 0) recv = borderD_tag;
+            const uint32_t inG = __byte_perm(recv, eG, 0x5410);
+            const uint32_t inD = __byte_perm(recv, eD, 0x5432);
+            if ((unsigned)(k - kfirst) <= (unsigned)n) {
+                const uint32_t rlo = rrp[k], rhi = LUT ? rrp[k - 1] : 0u;
+                uint32_t hd = diag, dv = inD;
+                uint32_t acc[NW + 1];
+#pragma unroll
+                for (int c = 0; c < CS; c++) {
+                    const uint32_t sc = subst_score<LUT>(q[c], rlo, rhi, ma16, mi16);
+                    const uint32_t mt = __viaddmax_s16x2(hd, sc, Bp) | 0x000f000fu;
+                    hd = Gup[c];
+                    const uint32_t iv = __viaddmax_s16x2(IcUp[c], ge16, IoUp[c]);
+                    const uint32_t g = __vimax3_s16x2(mt, iv, dv);
+                    const uint32_t code = (g & 0x000c000cu) | ((iv | dv) & 0x00030003u);
+                    if ((c & 3) == 0) acc[c >> 2] = code; else acc[c >> 2] = acc[c >> 2] * 16u + code;
+                    Gup[c] = g;
+                    IoUp[c] = (uint32_t)((int)mt * ONE + KI);
+                    IcUp[c] = iv & 0xfffdfffdu;
+                    dv = __viaddmax_s16x2(dv & 0xfffefffeu, ge16, (uint32_t)((int)mt * ONE + KD));
+                }
+                eG = Gup[CS - 1];
+                eD = dv;
+                diag = inG;
+                if (k >= kstore) {
+#pragma unroll
+                    for (int x = 0; x < NW; x++) wptr[x] = acc[x];
+                    if (R) *hptr = (uint16_t)((acc[NW] & 0xffu) | ((acc[NW] >> 8) & 0xff00u));
+                }
+                if (k == kc) {
+                    uint32_t gsel = 0;
+#pragma unroll
+                    for (int c = 0; c < CS; c++) if (c == c_col) gsel = Gup[c];
+                    corner16 = (int)(short)(c_half ? (gsel >> 16) : (gsel & 0xffffu));
+                }
+            }
+            wptr += dw.nl * NW;
+            hptr += dw.nl;
+        }
+        int corner = (__shfl_sync(FULL, corner16, segbase + c_lane) - B) >> 4;
+        if (!work) corner = 0;
+        __threadfence_block();
+        __syncwarp();
+
+        // ---------------- traceback, align.cpp:185-230, LANES lanes per tile ----------------
+        // (see traceback_tile16 in gact_kernels_s16.cuh; here both segments run side by side, so the
+        //  M-run evaluation is executed by every lane and only applied where the segment is in state M)
+        {
+            uint8_t *stbuf = reinterpret_cast<uint8_t *>(rr);      // rr[] is dead now
+            const int ma = P.match, mi = P.mismatch, go = P.gap_open, ge = P.gap_extend;
+            const int i0 = dw.i0, j0 = max(m - et, 1);
+            int i = n, j = m, cnt = 0, v = corner, ri = et, rj = et;
+            int state = (work && v > 0) ? (dw.load(i, j) >> 2) : 0;
+            bool act = (state != 0);
+            while (__any_sync(FULL, act)) {
+                const bool inM = act && state == 3;
+                const int it = i - sl, jt = j - sl;
+                const bool inb = inM && it >= i0 && jt >= j0;
+                const int code_t = inb ? dw.load(it, jt) : 0;
+                const bool match_t = inb && (rb[it] == qs[jt]);
+                const unsigned mm = (__ballot_sync(FULL, match_t) >> segbase) & SEGMASK;
+                const int below = __popc(mm & ((1u << sl) - 1u));
+                const int v_t = v - (below * ma + (sl - below) * mi);
+                const bool isM_t = (sl == 0) || (inb && v_t > 0 && (code_t >> 2) == 3);
+                const unsigned run = (__ballot_sync(FULL, isM_t) >> segbase) & SEGMASK;
+                int L = __ffs(~run) - 1;
+                if (L < 0 || L > LANES - 1) L = LANES - 1;
+                L = min(L, min(ri, rj));
+                const int codeL = __shfl_sync(FULL, code_t, segbase + L);
+                if (inM) {
+                    if (sl < L) stbuf[cnt + sl] = 3;
+                    const int bl = __popc(mm & ((1u << L) - 1u));
+                    cnt += L; ri -= L; rj -= L;
+                    v -= bl * ma + (L - bl) * mi;
+                    i -= L; j -= L;
+                    state = (i >= i0 && j >= j0 && v > 0) ? (codeL >> 2) : 0;
+                } else if (act) {
+                    const int code = dw.load(i, j);
+                    const bool open = (state == 2) ? (code & 2) : (code & 1);
+                    if (sl == 0) stbuf[cnt] = (uint8_t)state;
+                    cnt++;
+                    v -= open ? go : ge;
+                    if (state == 2) { i--; ri--; } else { j--; rj--; }
+                    state = open ? 3 : state;
+                    if (i <= 0 || j <= 0) state = 0;
+                }
+                act = (state != 0 && ri > 0 && rj > 0);
+            }
+            __syncwarp();
+            if (valid) {
+                uint32_t *out = states + (size_t)t * pitch_words;
+                for (int w = sl; w * 16 < cnt; w += LANES) {
+                    uint32_t a = 0;
+#pragma unroll
+                    for (int x = 0; x < 16; x++) {
+                        const int idx = w * 16 + x;
+                        const uint32_t st = (idx < cnt) ? stbuf[idx] : 0u;
+                        a |= st << (2 * x);
+                    }
+                    out[w] = a;
+                }
+                if (sl == 0) {
+                    gact_tile_result r;
+                    r.score = corner;
+                    r.max_i = d.first ? n : d.ref_len;
+                    r.max_j = d.first ? m : d.query_len;
+                    r.n_states = cnt;
+                    r.i_steps = et - ri;
+                    r.j_steps = et - rj;
+                    results[t] = r;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+struct S16HPlan {
+    bool ok = false;
+    int CS = 0, lanes = 16, win_rows = 0, win_lanes = 0, warps_per_cta = 4, ctas = 0, bias = 0;
+    bool lut_ok = false;
+    size_t seq_bytes = 0, smem = 0, dir_bytes = 0;
+    uint8_t *d_scratch = nullptr;
+};
+
+typedef void (*s16h_fn)(const KParams, const gact_tile_desc *, const int *, int, const EffLen *, gact_tile_result *,
+                        uint32_t *, int, int *, size_t, uint8_t *, size_t);
+inline s16h_fn s16h_pick(int CS, bool lut)
+{
+    switch (CS) {
+        case 8: return lut ? gact_tile_s16h_kernel<8, 16, true> : gact_tile_s16h_kernel<8, 16, false>;
+        case 10: return lut ? gact_tile_s16h_kernel<10, 16, true> : gact_tile_s16h_kernel<10, 16, false>;
+        default: return nullptr;
+    }
+}
+
+inline void s16h_free_plan(S16HPlan *pl)
+{
+    if (pl->d_scratch) cudaFree(pl->d_scratch);
+    pl->d_scratch = nullptr;
+}
+
+// Two tiles per warp for tile_size <= 320 (CS = 8 up to 256, CS = 10 up to 320).
+inline int s16h_make_plan(const gact_params &p, int num_sms, int warps_per_sm, S16HPlan *pl)
+{
+    s16h_free_plan(pl);
+    *pl = S16HPlan();
+    const int T = p.tile_size, et = p.tile_size - p.tile_overlap;
+    if (T > 320) return 0;
+    const int bias = 16 * (-p.gap_open + 2);
+    pl->bias = bias;
+    pl->lut_ok = (p.match * 16 <= 127 && p.mismatch * 16 >= -128);
+    const long hi = (long)T * (p.match > 0 ? p.match : 0) * 16 + 16 + bias;
+    if (hi > 30000 || p.mismatch > 0 || p.match < 0 || p.gap_open < -500 || p.gap_extend < -500 || p.mismatch < -1000)
+        return 0;
+    const int CS = (T <= 256) ? 8 : 10;
+    pl->CS = CS;
+    pl->win_rows = (et + 1 < T) ? et + 1 : T;
+    int wl = et / (2 * CS) + 2;
+    pl->win_lanes = wl > 16 ? 16 : wl;
+    const int TS = CS * 32;
+    pl->seq_bytes = (size_t)(((TS + 2) * 8 + 15) & ~15);
+    pl->dir_bytes = (CS == 8) ? DirWinH<8>::bytes(pl->win_rows, pl->win_lanes) : DirWinH<10>::bytes(pl->win_rows, pl->win_lanes);
+    int wps = warps_per_sm > 0 ? warps_per_sm : 16;
+    if (wps > 16) wps = 16;
+    pl->warps_per_cta = 4;
+    const int c = (wps + 3) / 4;
+    pl->ctas = c * num_sms;
+    pl->smem = (size_t)pl->warps_per_cta * 2 * pl->seq_bytes;
+    const size_t total = (size_t)pl->ctas * pl->warps_per_cta * 2 * pl->dir_bytes;
+    if (cudaMalloc(&pl->d_scratch, total) != cudaSuccess) { cudaGetLastError(); pl->d_scratch = nullptr; return 0; }
+    for (int lut = 0; lut < 2; lut++)
+        if (cudaFuncSetAttribute((const void *)s16h_pick(CS, lut != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)pl->smem) != cudaSuccess)
+            return -1;
+    pl->ok = true;
+    return 0;
+}
+
+inline void s16h_launch(const S16HPlan &pl, KParams kp, const gact_tile_desc *descs, const int *order, int n,
+                        const EffLen *eff, gact_tile_result *results, uint32_t *states, int pitch_words, int *counter,
+                        cudaStream_t st)
+{
+    kp.win_rows = pl.win_rows;
+    kp.win_lanes = pl.win_lanes;
+    kp.s16_bias = pl.bias;
+    kp.one = 1;
+    bool lut = pl.lut_ok;
+    for (int i = 0; i < GACT_MAX_SETS; i++) if (kp.sets[i].bytes) lut = false;
+    int ctas = pl.ctas;
+    const int need = (n + pl.warps_per_cta * 2 - 1) / (pl.warps_per_cta * 2);
+    if (need < ctas) ctas = need;
+    s16h_pick(pl.CS, lut)<<<ctas, pl.warps_per_cta * 32, pl.smem, st>>>(kp, descs, order, n, eff, results, states,
+                                                                       pitch_words, counter, pl.seq_bytes,
+                                                                       pl.d_scratch, pl.dir_bytes);
+}
+
+}  // namespace gact
