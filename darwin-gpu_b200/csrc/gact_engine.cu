@@ -39,7 +39,7 @@ struct Slot {
     int *d_first = nullptr, *h_first = nullptr;
     int *d_order = nullptr, *h_order = nullptr;      // tiles by descending reference length (pairs similar tiles)
     int *d_counters = nullptr;            // [0] first pass, [1] main pass
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr, ev_h2d = nullptr;
     int n = 0, n_first = 0;
     bool busy = false;
     unsigned long long cells = 0;
@@ -51,6 +51,7 @@ struct gact_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams: descriptor upload / result download overlap the kernels
     gact_params params{};
     KParams kp{};
     int max_tiles = 0;
@@ -144,6 +145,7 @@ void free_slot(Slot &s)
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
+    if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
     s = Slot();
 }
 
@@ -319,10 +321,14 @@ int enqueue(gact_engine *e, Slot &s, int n, const gact_tile_desc *descs)
     s.n = n;
     if (n == 0) return GACT_OK;
     memcpy(s.h_descs, descs, (size_t)n * sizeof(gact_tile_desc));
-    CU(e, cudaMemcpyAsync(s.d_descs, s.h_descs, (size_t)n * sizeof(gact_tile_desc), cudaMemcpyHostToDevice, e->stream));
+    // upload on the H2D copy stream; the compute stream waits for it, so the copy of batch k+1
+    // overlaps the kernels of batch k
+    CU(e, cudaMemcpyAsync(s.d_descs, s.h_descs, (size_t)n * sizeof(gact_tile_desc), cudaMemcpyHostToDevice, e->s_h2d));
     if (s.n_first)
-        CU(e, cudaMemcpyAsync(s.d_first, s.h_first, (size_t)s.n_first * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    CU(e, cudaMemcpyAsync(s.d_order, s.h_order, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+        CU(e, cudaMemcpyAsync(s.d_first, s.h_first, (size_t)s.n_first * sizeof(int), cudaMemcpyHostToDevice, e->s_h2d));
+    CU(e, cudaMemcpyAsync(s.d_order, s.h_order, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, e->s_h2d));
+    CU(e, cudaEventRecord(s.ev_h2d, e->s_h2d));
+    CU(e, cudaStreamWaitEvent(e->stream, s.ev_h2d, 0));
     e->stats.h2d_bytes += (double)n * (sizeof(gact_tile_desc) + sizeof(int)) + (double)s.n_first * sizeof(int);
     return GACT_OK;
 }
@@ -330,10 +336,13 @@ int enqueue(gact_engine *e, Slot &s, int n, const gact_tile_desc *descs)
 int download(gact_engine *e, Slot &s, bool want_states)
 {
     if (s.n == 0) return GACT_OK;
-    CU(e, cudaMemcpyAsync(s.h_results, s.d_results, (size_t)s.n * sizeof(gact_tile_result), cudaMemcpyDeviceToHost, e->stream));
+    // download on the D2H copy stream once the kernels of this batch are done (ev_k1), so the
+    // next batch's kernels do not wait for the copy
+    CU(e, cudaStreamWaitEvent(e->s_d2h, s.ev_k1, 0));
+    CU(e, cudaMemcpyAsync(s.h_results, s.d_results, (size_t)s.n * sizeof(gact_tile_result), cudaMemcpyDeviceToHost, e->s_d2h));
     e->stats.d2h_bytes += (double)s.n * sizeof(gact_tile_result);
     if (want_states) {
-        CU(e, cudaMemcpyAsync(s.h_states, s.d_states, (size_t)s.n * e->pitch_words * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU(e, cudaMemcpyAsync(s.h_states, s.d_states, (size_t)s.n * e->pitch_words * 4, cudaMemcpyDeviceToHost, e->s_d2h));
         e->stats.d2h_bytes += (double)s.n * e->pitch_words * 4;
     }
     return GACT_OK;
@@ -427,6 +436,8 @@ int gact_engine_create(gact_engine **out, int device, const gact_params *p, int 
         e->num_sms = prop.multiProcessorCount;
         if (stream) { e->stream = (cudaStream_t)stream; e->owns_stream = false; }
         else { CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->owns_stream = true; }
+        CK(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
 
         const int et = p->tile_size - p->tile_overlap;
         e->pitch_words = (2 * et + 15) / 16 + 1;
@@ -456,6 +467,7 @@ int gact_engine_create(gact_engine **out, int device, const gact_params *p, int 
             CK(cudaEventCreate(&s.ev_k0));
             CK(cudaEventCreate(&s.ev_k1));
             CK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
         }
     }
 #undef CK
@@ -476,6 +488,8 @@ void gact_engine_destroy(gact_engine *e)
     if (e->d_gscratch) cudaFree(e->d_gscratch);
     s16_free_plan(&e->s16);
     s16h_free_plan(&e->s16h);
+    if (e->s_h2d) { cudaStreamSynchronize(e->s_h2d); cudaStreamDestroy(e->s_h2d); }
+    if (e->s_d2h) { cudaStreamSynchronize(e->s_d2h); cudaStreamDestroy(e->s_d2h); }
     if (e->owns_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -592,7 +606,7 @@ int gact_engine_submit(gact_engine *e, int n, const gact_tile_desc *descs)
         rc = download(e, s, true);
         if (rc) return rc;
     }
-    CU(e, cudaEventRecord(s.ev_done, e->stream));
+    CU(e, cudaEventRecord(s.ev_done, n > 0 ? e->s_d2h : e->stream));
     s.busy = true;
     e->head ^= 1;
     e->inflight++;
@@ -606,6 +620,22 @@ int gact_engine_wait(gact_engine *e, gact_tile_result *results, uint32_t *packed
     CU(e, cudaSetDevice(e->device));
     Slot &s = e->slots[e->tail];
     int rc = finish(e, s, results, packed_states, true);
+    s.busy = false;
+    e->tail ^= 1;
+    e->inflight--;
+    return rc;
+}
+
+int gact_engine_wait_view(gact_engine *e, int *n, const gact_tile_result **results, const uint32_t **packed_states)
+{
+    if (!e) return GACT_ERR_ARG;
+    if (e->inflight == 0) return fail(e, GACT_ERR_STATE, "wait without submit");
+    CU(e, cudaSetDevice(e->device));
+    Slot &s = e->slots[e->tail];
+    int rc = finish(e, s, nullptr, nullptr, false);
+    if (n) *n = s.n;
+    if (results) *results = s.h_results;
+    if (packed_states) *packed_states = s.h_states;
     s.busy = false;
     e->tail ^= 1;
     e->inflight--;
@@ -628,7 +658,7 @@ int gact_engine_align_tiles(gact_engine *e, int n, const gact_tile_desc *descs,
         rc = download(e, s, packed_states != nullptr);
         if (rc) return rc;
     }
-    CU(e, cudaEventRecord(s.ev_done, e->stream));
+    CU(e, cudaEventRecord(s.ev_done, n > 0 ? e->s_d2h : e->stream));
     return finish(e, s, results, packed_states, packed_states != nullptr);
 }
 
@@ -640,6 +670,7 @@ int gact_engine_stage(gact_engine *e, int n, const gact_tile_desc *descs)
     Slot &s = e->slots[0];
     int rc = enqueue(e, s, n, descs);
     if (rc) return rc;
+    CU(e, cudaStreamSynchronize(e->s_h2d));
     CU(e, cudaStreamSynchronize(e->stream));
     e->staged = true;
     return GACT_OK;
@@ -692,6 +723,7 @@ int gact_engine_fetch_staged(gact_engine *e, gact_tile_result *results, uint32_t
     Slot &s = e->slots[0];
     int rc = download(e, s, packed_states != nullptr);
     if (rc) return rc;
+    CU(e, cudaStreamSynchronize(e->s_d2h));
     CU(e, cudaStreamSynchronize(e->stream));
     if (s.n > 0) {
         if (results) memcpy(results, s.h_results, (size_t)s.n * sizeof(gact_tile_result));

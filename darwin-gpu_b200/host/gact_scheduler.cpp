@@ -224,15 +224,18 @@ void GactScheduler::run(const std::vector<GactCall> &calls, std::vector<GactAlig
     };
     auto wait_and_consume = [&](Group &g) {
         const size_t n = g.descs.size();
-        g.res.resize(n);
-        g.st.resize(n * (size_t)pitch_);
-        int rc = gact_engine_wait(eng_, g.res.data(), g.st.data());
-        if (rc) fail(eng_, "gact_engine_wait", rc);
+        // zero-copy: read results and states straight from the engine's pinned buffers
+        const gact_tile_result *res = nullptr;
+        const uint32_t *st = nullptr;
+        int got = 0;
+        int rc = gact_engine_wait_view(eng_, &got, &res, &st);
+        if (rc) fail(eng_, "gact_engine_wait_view", rc);
+        if ((size_t)got != n) throw std::runtime_error("GactScheduler: batch size mismatch");
         g.inflight = false;
         g.adv.assign(n, 0);
         parallel_for(threads_, n, [&](size_t a, size_t b) {
             for (size_t k = a; k < b; k++)
-                g.adv[k] = consume(act[g.owner[k]], g.res[k], g.st.data() + k * (size_t)pitch_) ? 1 : 0;
+                g.adv[k] = consume(act[g.owner[k]], res[k], st + k * (size_t)pitch_) ? 1 : 0;
         });
     };
 

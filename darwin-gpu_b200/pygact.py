@@ -49,7 +49,7 @@ EXPORTS = [
     "gact_abi_version", "gact_status_string", "gact_device_count", "gact_engine_create",
     "gact_engine_destroy", "gact_last_error", "gact_engine_upload", "gact_engine_seq_start",
     "gact_engine_set_length", "gact_engine_set_bits", "gact_engine_states_pitch_words",
-    "gact_engine_max_tiles", "gact_engine_align_tiles", "gact_engine_submit", "gact_engine_wait",
+    "gact_engine_max_tiles", "gact_engine_align_tiles", "gact_engine_submit", "gact_engine_wait", "gact_engine_wait_view",
     "gact_engine_stage", "gact_engine_run_staged", "gact_engine_fetch_staged", "gact_engine_sync",
     "gact_engine_last_kernel_ms", "gact_engine_stats", "gact_engine_reset_stats",
     "gact_engine_set_kernel", "gact_engine_get_kernel", "gact_int_peak",
@@ -96,6 +96,8 @@ def load():
     L.gact_engine_submit.argtypes = [vp, i32, vp]
     L.gact_engine_wait.restype = i32
     L.gact_engine_wait.argtypes = [vp, vp, vp]
+    L.gact_engine_wait_view.restype = i32
+    L.gact_engine_wait_view.argtypes = [vp, C.POINTER(i32), C.POINTER(vp), C.POINTER(vp)]
     L.gact_engine_stage.restype = i32
     L.gact_engine_stage.argtypes = [vp, i32, vp]
     L.gact_engine_run_staged.restype = i32
@@ -218,11 +220,14 @@ class GactEngine:
         self._ck(self.L.gact_engine_submit(self.h, len(descs), descs.ctypes.data), "gact_engine_submit")
         self._last_n.append(len(descs))
 
-    def wait(self):
+    def wait(self, out_res=None, out_st=None):
+        """Results of the oldest outstanding batch; optionally into caller-provided arrays."""
         n = self._last_n.pop(0) if getattr(self, "_last_n", None) else 0
-        res, st = self._bufs(n)
-        self._ck(self.L.gact_engine_wait(self.h, res.ctypes.data, st.ctypes.data), "gact_engine_wait")
-        return res, st
+        if out_res is None:
+            out_res, out_st = self._bufs(n)
+        assert len(out_res) == n and out_res.flags.c_contiguous and out_st.flags.c_contiguous
+        self._ck(self.L.gact_engine_wait(self.h, out_res.ctypes.data, out_st.ctypes.data), "gact_engine_wait")
+        return out_res, out_st
 
     def stage(self, descs):
         descs = np.ascontiguousarray(descs, dtype=TILE_DESC_DTYPE)

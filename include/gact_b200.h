@@ -172,6 +172,12 @@ int gact_engine_align_tiles(gact_engine *e, int n, const gact_tile_desc *descs,
 int gact_engine_submit(gact_engine *e, int n, const gact_tile_desc *descs);
 int gact_engine_wait(gact_engine *e, gact_tile_result *results, uint32_t *packed_states);
 
+/* Like gact_engine_wait(), but hands out pointers into the engine's pinned result buffers
+ * instead of copying (n tiles; states rows gact_engine_states_pitch_words() apart).  The
+ * pointers stay valid until the second gact_engine_submit() after this call. */
+int gact_engine_wait_view(gact_engine *e, int *n, const gact_tile_result **results,
+                          const uint32_t **packed_states);
+
 /* Device-resident form (benchmarks, on-device pipelines): stage() copies the
  * descriptors once, run_staged() only launches the kernels (asynchronous on
  * the engine stream), fetch_staged() synchronises and copies results out. */
