@@ -259,7 +259,10 @@ int launch_batch(gact_engine *e, Slot &s)
     CU(e, cudaMemsetAsync(s.d_counters, 0, 2 * sizeof(int), st));
     CU(e, cudaEventRecord(s.ev_k0, st));
     const int TS = e->C * 32;
-    if (s.n_first > 0) {
+    if (s.n_first > 0 && use_s16(e) && e->s16h.ok) {
+        s16h_launch_first(e->s16h, e->kp, s.d_descs, s.d_first, s.n_first, s.d_eff, s.d_counters + 0, st);
+        e->stats.kernel_launches++;
+    } else if (s.n_first > 0) {
         first_fn ff = pick_first_i32(e->C);
         int ctas = e->num_sms * 4;
         int need = (s.n_first + 7) / 8;

@@ -278,7 +278,9 @@ gact_tile_s16_kernel(const __grid_constant__ KParams P, const gact_tile_desc *__
             IcUp[c] = pk16(S16_NEG, S16_NEG);
         }
         uint32_t eG = Bp, eD = pk16(S16_NEG), diag = Bp;
-        const int k1 = min(dw.i0 - 1, steps);                  // phase 1 covers steps 1..k1 (all rows < i0)
+        // phase 1 covers steps 1..k1: the first lane that keeps direction codes (lane0) reaches
+        // window row i0 at step i0 + 2*lane0
+        const int k1 = min(dw.i0 - 1 + 2 * dw.lane0, steps);
         int k = 1;
         for (; k <= k1; k++) {
             const uint32_t pack = __byte_perm(eG, eD, 0x7632);

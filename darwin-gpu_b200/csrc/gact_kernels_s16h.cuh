@@ -144,7 +144,9 @@ gact_tile_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *_
         const int kc = n + 2 * c_lane + c_half;
         const bool work = (n > 0 && m > 0);
         const int steps_seg = work ? n + 1 + 2 * lastlane : 0;
-        int steps = steps_seg, k1 = work ? min(dw.i0 - 1, steps_seg) : 0x3fffffff;
+        // the first lane that keeps direction codes (lane0) reaches window row i0 at step i0 + 2*lane0;
+        // until then every lane can stay in the cheaper untagged loop
+        int steps = steps_seg, k1 = work ? min(dw.i0 - 1 + 2 * dw.lane0, steps_seg) : 0x3fffffff;
 #pragma unroll
         for (int o = LANES; o < 32; o <<= 1) {
             steps = max(steps, __shfl_xor_sync(FULL, steps, o));
@@ -324,6 +326,165 @@ gact_tile_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *_
 }
 
 // ---------------------------------------------------------------------------
+// First-tile pass in the packed domain: score only, plus the position of the LAST maximum in
+// (i outer, j inner) order (align.cpp:173-177).  Per column and half-word the running maximum
+// and the row where it was last reached are kept (VIMNMX.S16x2 with predicate outputs = the
+// reference's `>=` update); columns are then compared by (H, i, j).
+template <int CS, int LANES, bool LUT>
+__global__ void __launch_bounds__(128, 4)
+gact_first_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *__restrict__ descs,
+                       const int *__restrict__ first_list, int n_first, EffLen *__restrict__ eff, int *counter,
+                       size_t seq_bytes)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int TPW = 32 / LANES;
+    constexpr int TS = CS * 2 * LANES;
+    int lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    const int warp = threadIdx.x >> 5;
+    const int seg = lane / LANES, sl = lane % LANES;
+
+    uint8_t *my = smem + ((size_t)warp * TPW + seg) * seq_bytes;
+    uint32_t *rr = reinterpret_cast<uint32_t *>(my);
+    uint16_t *qs = reinterpret_cast<uint16_t *>(my + (TS + 2) * 4);
+    uint16_t *rb = reinterpret_cast<uint16_t *>(my + (TS + 2) * 6);
+
+    const int B = P.s16_bias;
+    const uint32_t Bp = pk16(B);
+    const uint32_t ma16 = pk16(P.match * 16), mi16 = pk16(P.mismatch * 16);
+    const uint32_t ge16 = pk16(P.gap_extend * 16);
+    const int KO = (P.gap_open * 16) * 65537;
+    const int ONE = P.one;
+    const uint32_t borderD_raw = ((uint32_t)(B + P.gap_open * 16) << 16) | (uint32_t)B;
+    const uint32_t lut_mis = (uint32_t)((P.mismatch * 16) & 0xff) * 0x01010101u;
+
+    for (;;) {
+        int t0 = 0;
+        if (lane == 0) t0 = atomicAdd(counter, TPW);
+        t0 = __shfl_sync(FULL, t0, 0);
+        if (t0 >= n_first) break;
+        const bool valid = (t0 + seg) < n_first;
+        const int t = valid ? first_list[t0 + seg] : 0;
+        gact_tile_desc d;
+        d.ref_off = 0; d.query_off = 0; d.ref_len = 0; d.query_len = 0; d.ref_set = 0; d.query_set = 0; d.reverse = 0; d.first = 0;
+        if (valid) d = descs[t];
+        const int n = d.ref_len, m = d.query_len;
+        const SeqSetDev &rset = P.sets[d.ref_set];
+        const SeqSetDev &qset = P.sets[d.query_set];
+        const bool work = (n > 0 && m > 0);
+
+        __syncwarp();
+        if (work) {
+            for (int x = sl; x <= n + 1; x += LANES) {
+                const bool in = (x >= 1 && x <= n);
+                const int base = in ? tile_base(rset, d.ref_off, d.ref_len, d.reverse, x) : 0;
+                rb[x] = (uint16_t)(in ? enc_base(base) : SENT_R);
+                if (LUT) {
+                    const int code = (base == 'A') ? 0 : (base == 'C') ? 1 : (base == 'G') ? 2 : (base == 'T') ? 3 : 4;
+                    uint32_t w = lut_mis;
+                    if (in && code < 4) w ^= (uint32_t)(((P.match ^ P.mismatch) * 16) & 0xff) << (8 * code);
+                    rr[x] = w;
+                }
+            }
+            for (int x = sl; x <= m; x += LANES)
+                qs[x] = (x >= 1) ? (uint16_t)enc_base(tile_base(qset, d.query_off, d.query_len, d.reverse, x)) : (uint16_t)SENT_Q;
+        }
+        __syncwarp();
+        if (!LUT && work) {
+            for (int x = sl; x <= n + 1; x += LANES)
+                rr[x] = (uint32_t)rb[x] | ((uint32_t)(x >= 1 ? rb[x - 1] : (uint16_t)SENT_R) << 16);
+        }
+        __syncwarp();
+
+        uint32_t q[CS];
+#pragma unroll
+        for (int c = 0; c < CS; c++) {
+            const int jl = (2 * sl) * CS + c + 1, jh = (2 * sl + 1) * CS + c + 1;
+            const uint32_t el = jl <= m ? (uint32_t)qs[jl] : SENT_Q + c, eh = jh <= m ? (uint32_t)qs[jh] : SENT_Q + c;
+            if (LUT) {
+                const uint32_t tl = (el >> 1) & 3u, th = (eh >> 1) & 3u;
+                const uint32_t l2 = (jl <= m) ? (tl ^ (tl >> 1)) : 0u, h2 = (jh <= m) ? (th ^ (th >> 1)) : 0u;
+                q[c] = l2 | ((8u | l2) << 4) | ((4u | h2) << 8) | ((12u | h2) << 12);
+            } else {
+                q[c] = el | (eh << 16);
+            }
+        }
+        const int laststrip = (m > 0) ? (m - 1) / CS : -1;
+        const int lastlane = laststrip >> 1;
+        int steps = work ? n + 1 + 2 * lastlane : 0;
+#pragma unroll
+        for (int o = LANES; o < 32; o <<= 1) steps = max(steps, __shfl_xor_sync(FULL, steps, o));
+        const int kfirst = (work && sl <= lastlane) ? 2 * sl + 1 : 0x3fffffff;
+        const uint32_t *rrp = rr - 2 * sl;
+
+        uint32_t Gup[CS], IoUp[CS], IcUp[CS], best[CS], brow[CS];
+#pragma unroll
+        for (int c = 0; c < CS; c++) {
+            Gup[c] = Bp;
+            IoUp[c] = pk16(B + P.gap_open * 16, S16_NEG);
+            IcUp[c] = pk16(S16_NEG, S16_NEG);
+            best[c] = 0;                               // below every H (H >= B > 0): the first valid cell always updates
+            brow[c] = 0;
+        }
+        uint32_t eG = Bp, eD = pk16(S16_NEG), diag = Bp;
+        for (int k = 1; k <= steps; k++) {
+            const uint32_t pack = __byte_perm(eG, eD, 0x7632);
+            uint32_t recv = __shfl_up_sync(FULL, pack, 1, LANES);
+            if (sl == 0) recv = borderD_raw;
+            const uint32_t inG = __byte_perm(recv, eG, 0x5410);
+            const uint32_t inD = __byte_perm(recv, eD, 0x5432);
+            const int ilo = k - 2 * sl;
+            if ((unsigned)(k - kfirst) <= (unsigned)n) {
+                const uint32_t rlo = rrp[k], rhi = LUT ? rrp[k - 1] : 0u;
+                // rows that do not exist (low half: row n+1, high half: row 0) must not be recorded
+                const uint32_t keep = ((ilo <= n) ? 0x0000ffffu : 0u) | ((ilo >= 2) ? 0xffff0000u : 0u);
+                const uint32_t ipair = pk16(ilo, ilo - 1);
+                uint32_t hd = diag, dv = inD;
+#pragma unroll
+                for (int c = 0; c < CS; c++) {
+                    const uint32_t sc = subst_score<LUT>(q[c], rlo, rhi, ma16, mi16);
+                    const uint32_t mc = __viaddmax_s16x2(hd, sc, Bp);
+                    hd = Gup[c];
+                    const uint32_t iv = __viaddmax_s16x2(IcUp[c], ge16, IoUp[c]);
+                    const uint32_t h = __vimax3_s16x2(mc, iv, dv);
+                    Gup[c] = h;
+                    const uint32_t mo = (uint32_t)((int)mc * ONE + KO);
+                    IoUp[c] = mo;
+                    IcUp[c] = iv;
+                    dv = __viaddmax_s16x2(dv, ge16, mo);
+                    bool ph, pl;
+                    best[c] = __vibmax_s16x2(h & keep, best[c], &ph, &pl);      // pred = (h >= best): last maximum wins
+                    if (pl) brow[c] = __byte_perm(brow[c], ipair, 0x3254);
+                    if (ph) brow[c] = __byte_perm(brow[c], ipair, 0x7610);
+                }
+                eG = Gup[CS - 1];
+                eD = dv;
+                diag = inG;
+            }
+        }
+        // best cell of this lane by (H, i, j); j <= 320 and i <= 320 take 9 bits each here
+        int key = -1;
+#pragma unroll
+        for (int c = 0; c < CS; c++) {
+            const int jl = (2 * sl) * CS + c + 1, jh = (2 * sl + 1) * CS + c + 1;
+            const int hl = (int)(best[c] & 0xffffu), hh = (int)(best[c] >> 16);
+            const int il = (int)(brow[c] & 0xffffu), ih = (int)(brow[c] >> 16);
+            if (work && jl <= m && il >= 1) key = max(key, (((hl - B) >> 4) << 18) | (il << 9) | jl);
+            if (work && jh <= m && ih >= 1) key = max(key, (((hh - B) >> 4) << 18) | (ih << 9) | jh);
+        }
+#pragma unroll
+        for (int o = 1; o < LANES; o <<= 1) key = max(key, __shfl_xor_sync(FULL, key, o));
+        if (valid && sl == 0) {
+            EffLen e;
+            if (key < 0) { e.n = 0; e.m = 0; }
+            else { e.m = key & 511; e.n = (key >> 9) & 511; }
+            eff[t] = e;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 struct S16HPlan {
     bool ok = false;
@@ -340,6 +501,16 @@ inline s16h_fn s16h_pick(int CS, bool lut)
     switch (CS) {
         case 8: return lut ? gact_tile_s16h_kernel<8, 16, true> : gact_tile_s16h_kernel<8, 16, false>;
         case 10: return lut ? gact_tile_s16h_kernel<10, 16, true> : gact_tile_s16h_kernel<10, 16, false>;
+        default: return nullptr;
+    }
+}
+
+typedef void (*s16h_first_fn)(const KParams, const gact_tile_desc *, const int *, int, EffLen *, int *, size_t);
+inline s16h_first_fn s16h_pick_first(int CS, bool lut)
+{
+    switch (CS) {
+        case 8: return lut ? gact_first_s16h_kernel<8, 16, true> : gact_first_s16h_kernel<8, 16, false>;
+        case 10: return lut ? gact_first_s16h_kernel<10, 16, true> : gact_first_s16h_kernel<10, 16, false>;
         default: return nullptr;
     }
 }
@@ -381,10 +552,26 @@ inline int s16h_make_plan(const gact_params &p, int num_sms, int warps_per_sm, S
     if (cudaMalloc(&pl->d_scratch, total) != cudaSuccess) { cudaGetLastError(); pl->d_scratch = nullptr; return 0; }
     for (int lut = 0; lut < 2; lut++)
         if (cudaFuncSetAttribute((const void *)s16h_pick(CS, lut != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)pl->smem) != cudaSuccess ||
+            cudaFuncSetAttribute((const void *)s16h_pick_first(CS, lut != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)pl->smem) != cudaSuccess)
             return -1;
     pl->ok = true;
     return 0;
+}
+
+inline void s16h_launch_first(const S16HPlan &pl, KParams kp, const gact_tile_desc *descs, const int *first_list,
+                              int n_first, EffLen *eff, int *counter, cudaStream_t st)
+{
+    kp.s16_bias = pl.bias;
+    kp.one = 1;
+    bool lut = pl.lut_ok;
+    for (int i = 0; i < GACT_MAX_SETS; i++) if (kp.sets[i].bytes) lut = false;
+    int ctas = pl.ctas;
+    const int need = (n_first + pl.warps_per_cta * 2 - 1) / (pl.warps_per_cta * 2);
+    if (need < ctas) ctas = need;
+    s16h_pick_first(pl.CS, lut)<<<ctas, pl.warps_per_cta * 32, pl.smem, st>>>(kp, descs, first_list, n_first, eff, counter,
+                                                                             pl.seq_bytes);
 }
 
 inline void s16h_launch(const S16HPlan &pl, KParams kp, const gact_tile_desc *descs, const int *order, int n,
