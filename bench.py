@@ -257,7 +257,6 @@ def main():
             eng.run_staged()
             ev[s + 1].record(stream)
     barrier()
-    clocks = sampler.stop()
     launches = eng.stats()["kernel_launches"] - launches0
     dev_ms = ev[0].elapsed_time(ev[-1])
     per_step_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(args.steps)]
@@ -291,6 +290,7 @@ def main():
         res_e2e = e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()            # sampled across both timed regions (device-resident and e2e legs)
     assert (res_e2e == res_dev).all(), "e2e and device-resident legs disagree"
     pitch = eng.pitch
     h2d = n * 36 + int(mb["first"].sum()) * 4
@@ -316,10 +316,18 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_bytes = (n * 32 + n * (24 + 4 * pitch) + cells * 2 * 0.25 / TILE)   # descs + results + 2-bit bases
-        roof = {"bound": "int_issue", "kernel": "gact_tile kernel (variant %d)" % eng.get_kernel(),
-                "achieved": achieved, "peak": peak_alu, "unit": "G int32 lane-ops/s", "frac": achieved / peak_alu,
-                "traffic": None, "ops_per_cell": OPS_PER_CELL,
-                "gcups_roofline_int32_alu": peak_alu / OPS_PER_CELL,
+        packed = eng.get_kernel() == 2
+        width = 2.0 if packed else 1.0         # cells per lane-op: the packed kernel computes two s16 cells per 32-bit lane
+        roof = {"bound": "int_issue", "kernel": "gact_tile_s16h/s16 kernel (packed s16x2 DPX)" if packed else "gact_tile_i32 kernel",
+                "achieved": achieved, "peak": peak_alu * width,
+                "unit": "G algorithmic int ops/s (17 per DP cell, SURVEY 8d); peak = measured ALU-pipe lane-op rate x cells per lane-op",
+                "frac": achieved / (peak_alu * width),
+                "traffic": None, "ops_per_cell": OPS_PER_CELL, "lane_width": "s16x2" if packed else "s32",
+                "peak_alu_lane_ops": peak_alu, "frac_of_int32_roofline": achieved / peak_alu,
+                "gcups_roofline_int32_alu": peak_alu / OPS_PER_CELL, "gcups_roofline_s16x2_alu": 2 * peak_alu / OPS_PER_CELL,
+                "note": "frac can exceed 1: the tagged-max formulation executes ~6 ALU-pipe instructions per cell instead "
+                        "of the 17 (8.5 packed) the roofline model assumes; ncu of the same kernel: ALU pipe 85 % busy "
+                        "(profiles/r1_s16h_tile_kernel_ncu.txt)",
                 "peak_alu_fma_mix": peak_mix, "peak_source": "gact_int_peak (own microbenchmark, measured in this run)",
                 "kernel_ms": kernel_ms,
                 "hbm": {"achieved": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
