@@ -16,6 +16,8 @@
 #include "gact_kernels_i32.cuh"
 #include "gact_kernels_s16.cuh"
 #include "gact_kernels_s16h.cuh"
+#include "dsoft.cuh"
+#include <algorithm>
 
 using namespace gact;
 
@@ -762,5 +764,147 @@ int gact_engine_get_kernel(const gact_engine *e)
     if (!e) return GACT_ERR_ARG;
     return use_s16(e) ? 2 : 1;
 }
+
+}  // extern "C"
+
+// ===========================================================================
+// D-SOFT on the device
+struct gact_dsoft {
+    gact_engine *e = nullptr;
+    DsoftParams p{};
+    uint32_t *d_index = nullptr, *d_pos = nullptr;
+    uint32_t *d_keys = nullptr, *d_touched = nullptr;
+    unsigned long long *d_vals = nullptr, *d_count = nullptr;
+    int *d_counter = nullptr;
+    DsoftQuery *d_queries = nullptr;
+    DsoftCand *d_out = nullptr;
+    size_t q_cap = 0, out_cap = 0;
+    int ctas = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = -1.0;
+};
+
+extern "C" {
+
+void gact_dsoft_destroy(gact_dsoft *d)
+{
+    if (!d) return;
+    cudaSetDevice(d->e->device);
+    cudaStreamSynchronize(d->e->stream);
+    cudaFree(d->d_index); cudaFree(d->d_pos); cudaFree(d->d_keys); cudaFree(d->d_touched); cudaFree(d->d_vals);
+    cudaFree(d->d_count); cudaFree(d->d_counter); cudaFree(d->d_queries); cudaFree(d->d_out);
+    if (d->ev0) cudaEventDestroy(d->ev0);
+    if (d->ev1) cudaEventDestroy(d->ev1);
+    delete d;
+}
+
+int gact_dsoft_create(gact_dsoft **out, gact_engine *e, const uint32_t *index_table, uint64_t index_entries,
+                      const uint32_t *pos_table, uint64_t n_pos, int kmer_size, int window_size,
+                      uint32_t bin_size, uint32_t kmer_max_occurence, int num_seeds, int threshold, int max_candidates)
+{
+    if (!out || !e || !index_table || (!pos_table && n_pos)) return GACT_ERR_ARG;
+    *out = nullptr;
+    if (kmer_size < 4 || kmer_size > 15 || window_size < 1 || window_size > 32 || window_size >= kmer_size ||
+        index_entries != ((uint64_t)1 << (2 * kmer_size)) + 1 || bin_size == 0 || num_seeds < 0 || threshold < 1)
+        return fail(e, GACT_ERR_ARG, "bad D-SOFT parameters");
+    CU(e, cudaSetDevice(e->device));
+    gact_dsoft *d = new (std::nothrow) gact_dsoft();
+    if (!d) return fail(e, GACT_ERR_NOMEM, "host allocation failed");
+    d->e = e;
+    d->ctas = e->num_sms * 2;
+    const size_t warps = (size_t)d->ctas * 4;
+    // every used seed can touch at most max_occ bins: size the per-warp table for the worst case, load <= 0.5
+    uint64_t need = 2ull * ((uint64_t)num_seeds + 2) * std::max<uint32_t>(kmer_max_occurence, 1u);
+    uint32_t cap = 1024;
+    while (cap < need && cap < (1u << 24)) cap <<= 1;
+    if (cap < need) { delete d; return fail(e, GACT_ERR_ARG, "D-SOFT table would exceed 16M slots per warp"); }
+    bool ok = cudaMalloc(&d->d_index, index_entries * 4) == cudaSuccess &&
+              cudaMalloc(&d->d_pos, std::max<uint64_t>(n_pos, 1) * 4) == cudaSuccess &&
+              cudaMalloc(&d->d_keys, warps * cap * 4) == cudaSuccess &&
+              cudaMalloc(&d->d_touched, warps * cap * 4) == cudaSuccess &&
+              cudaMalloc(&d->d_vals, warps * cap * 8) == cudaSuccess &&
+              cudaMalloc(&d->d_count, 8) == cudaSuccess && cudaMalloc(&d->d_counter, 4) == cudaSuccess &&
+              cudaEventCreate(&d->ev0) == cudaSuccess && cudaEventCreate(&d->ev1) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); gact_dsoft_destroy(d); return fail(e, GACT_ERR_NOMEM, "cudaMalloc(D-SOFT tables) failed"); }
+    cudaMemcpyAsync(d->d_index, index_table, index_entries * 4, cudaMemcpyHostToDevice, e->stream);
+    if (n_pos) cudaMemcpyAsync(d->d_pos, pos_table, n_pos * 4, cudaMemcpyHostToDevice, e->stream);
+    cudaMemsetAsync(d->d_keys, 0, warps * cap * 4, e->stream);
+    cudaError_t r = cudaStreamSynchronize(e->stream);
+    if (r != cudaSuccess) { gact_dsoft_destroy(d); return fail(e, GACT_ERR_CUDA, std::string("D-SOFT upload: ") + cudaGetErrorString(r)); }
+    e->stats.h2d_bytes += (double)(index_entries + n_pos) * 4;
+    d->p.index_table = d->d_index; d->p.pos_table = d->d_pos;
+    d->p.k = kmer_size; d->p.w = window_size; d->p.bin_size = bin_size; d->p.max_occ = kmer_max_occurence;
+    d->p.num_seeds = num_seeds; d->p.threshold = threshold; d->p.max_candidates = max_candidates;
+    d->p.table_cap = cap;
+    *out = d;
+    return GACT_OK;
+}
+
+int gact_dsoft_run(gact_dsoft *d, int n_queries, const int32_t *sets, const int64_t *seq_index,
+                   gact_dsoft_cand *out, int64_t out_cap, int64_t *n_out)
+{
+    if (!d || n_queries < 0 || (n_queries && (!sets || !seq_index)) || !n_out || out_cap < 0 || (out_cap && !out))
+        return GACT_ERR_ARG;
+    gact_engine *e = d->e;
+    *n_out = 0;
+    if (n_queries == 0) return GACT_OK;
+    CU(e, cudaSetDevice(e->device));
+    std::vector<DsoftQuery> q((size_t)n_queries);
+    for (int i = 0; i < n_queries; i++) {
+        const int s = sets[i];
+        if (s < 0 || s >= GACT_MAX_SETS) return fail(e, GACT_ERR_ARG, "bad set in D-SOFT query");
+        const SeqSetHost &hs = e->sets[s];
+        if (seq_index[i] < 0 || (size_t)seq_index[i] + 1 >= hs.starts.size()) return fail(e, GACT_ERR_ARG, "bad sequence index in D-SOFT query");
+        q[(size_t)i].start = hs.starts[(size_t)seq_index[i]];
+        q[(size_t)i].len = (int)(hs.starts[(size_t)seq_index[i] + 1] - hs.starts[(size_t)seq_index[i]]);
+        q[(size_t)i].set = s;
+    }
+    if ((size_t)n_queries > d->q_cap) {
+        cudaFree(d->d_queries);
+        d->d_queries = nullptr;
+        if (cudaMalloc(&d->d_queries, (size_t)n_queries * sizeof(DsoftQuery)) != cudaSuccess) { cudaGetLastError(); d->q_cap = 0; return fail(e, GACT_ERR_NOMEM, "cudaMalloc(queries) failed"); }
+        d->q_cap = (size_t)n_queries;
+    }
+    if ((size_t)out_cap > d->out_cap || !d->d_out) {
+        cudaFree(d->d_out);
+        d->d_out = nullptr;
+        const size_t want = std::max<size_t>((size_t)out_cap, 1024);
+        if (cudaMalloc(&d->d_out, want * sizeof(DsoftCand)) != cudaSuccess) { cudaGetLastError(); d->out_cap = 0; return fail(e, GACT_ERR_NOMEM, "cudaMalloc(candidates) failed"); }
+        d->out_cap = want;
+    }
+    for (int i = 0; i < GACT_MAX_SETS; i++) d->p.sets[i] = e->kp.sets[i];
+    cudaStream_t st = e->stream;
+    CU(e, cudaMemcpyAsync(d->d_queries, q.data(), (size_t)n_queries * sizeof(DsoftQuery), cudaMemcpyHostToDevice, st));
+    CU(e, cudaMemsetAsync(d->d_count, 0, 8, st));
+    CU(e, cudaMemsetAsync(d->d_counter, 0, 4, st));
+    CU(e, cudaEventRecord(d->ev0, st));
+    int ctas = d->ctas;
+    if ((n_queries + 3) / 4 < ctas) ctas = (n_queries + 3) / 4;
+    // the table area was sized for d->ctas CTAs of 4 warps; fewer CTAs use a prefix of it
+    dsoft_kernel<<<ctas, 128, 0, st>>>(d->p, d->d_queries, n_queries, d->d_keys, d->d_vals, d->d_touched,
+                                       d->d_out, (unsigned long long)std::min<size_t>((size_t)out_cap, d->out_cap), d->d_count, d->d_counter);
+    CU(e, cudaGetLastError());
+    CU(e, cudaEventRecord(d->ev1, st));
+    unsigned long long total = 0;
+    CU(e, cudaMemcpyAsync(&total, d->d_count, 8, cudaMemcpyDeviceToHost, st));
+    CU(e, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, d->ev0, d->ev1);
+    d->last_ms = ms;
+    e->stats.kernel_launches++;
+    *n_out = (int64_t)total;
+    if ((int64_t)total > out_cap) return fail(e, GACT_ERR_NOMEM, "candidate buffer too small (see *n_out)");
+    if (total) {
+        static_assert(sizeof(DsoftCand) == sizeof(gact_dsoft_cand), "candidate layouts differ");
+        CU(e, cudaMemcpy(out, d->d_out, (size_t)total * sizeof(DsoftCand), cudaMemcpyDeviceToHost));
+        std::sort(out, out + total, [](const gact_dsoft_cand &a, const gact_dsoft_cand &b) {
+            return a.query != b.query ? a.query < b.query : a.seq < b.seq;
+        });
+        e->stats.d2h_bytes += (double)total * sizeof(DsoftCand);
+    }
+    return GACT_OK;
+}
+
+double gact_dsoft_last_kernel_ms(const gact_dsoft *d) { return d ? d->last_ms : -1.0; }
 
 }  // extern "C"

@@ -10,6 +10,8 @@
 //   DARWIN_GPUS=<n>      GPUs to use (default: all visible); reads are sharded contiguously
 //                        by ceil(num_reads / n), one host scheduler thread + engine per GPU
 //   DARWIN_KERNEL=<0|1|2> kernel variant (auto / int32 / s16x2)
+//   DARWIN_DSOFT=<gpu|host> where the D-SOFT filter runs (default gpu: gact_dsoft_run on the shard's GPU;
+//                        host: SeedTable::dsoft on CPU_THREADS / n host threads)
 //
 // Flow per GPU shard: D-SOFT on the host for every read of the shard (CPU_THREADS / n
 // threads), then all candidates of the shard go through GactScheduler, then the overlap
@@ -55,6 +57,7 @@ struct Shard {
     uint64_t cand_fwd = 0, cand_rev = 0;
     std::string error;
     gact_engine *eng = nullptr;               // created before the align phase (like GPU_init, darwin.cpp:611)
+    gact_dsoft *dsoft = nullptr;              // device-side D-SOFT filter (optional)
 };
 
 int main(int argc, char **argv)
@@ -83,6 +86,7 @@ int main(int argc, char **argv)
     int want_gpus = ndev;
     if (const char *e = getenv("DARWIN_GPUS")) want_gpus = std::max(1, std::min(ndev, atoi(e)));
     const int kernel_variant = getenv("DARWIN_KERNEL") ? atoi(getenv("DARWIN_KERNEL")) : 0;
+    const bool dsoft_on_gpu = !(getenv("DARWIN_DSOFT") && std::string(getenv("DARWIN_DSOFT")) == "host");
     printf("Using GPU: %d device(s), CPU threads: %d\n", want_gpus, num_threads);
     printf("Scores: match = %d, mismatch = %d, gap_open = %d, gap_extend = %d\n", cfg.match, cfg.mismatch, cfg.gap_open, cfg.gap_extend);
     printf("Minimizer window size: %d\n", (int)cfg.window_size);
@@ -184,6 +188,25 @@ int main(int argc, char **argv)
     for (auto &sh : shards)
         if (!sh.error.empty()) { fprintf(stderr, "shard %d: %s\n", sh.tid, sh.error.c_str()); return 3; }
 
+    if (dsoft_on_gpu) {
+        // the seed-position table goes to every GPU once (index: 4^k + 1 words, positions: one word per minimizer)
+        auto t_up = Clock::now();
+        std::vector<std::thread> up;
+        for (auto &sh : shards) {
+            Shard *shp = &sh;
+            up.emplace_back([&, shp] {
+                int rc = gact_dsoft_create(&shp->dsoft, shp->eng, table->index_table(), table->index_entries(), table->pos_table(),
+                                           table->num_minimizers(), cfg.seed_size, (int)cfg.window_size, cfg.bin_size,
+                                           table->kmer_max_occurence(), cfg.num_seeds, cfg.threshold, cfg.max_candidates);
+                if (rc) shp->error = std::string("gact_dsoft_create: ") + gact_last_error(shp->eng);
+            });
+        }
+        for (auto &th : up) th.join();
+        std::cout << "Time elapsed (seed table upload to GPU): " << ms_since(t_up) << " msec" << std::endl;
+        for (auto &sh : shards)
+            if (!sh.error.empty()) { fprintf(stderr, "shard %d: %s\n", sh.tid, sh.error.c_str()); return 3; }
+    }
+
     std::vector<SeqView> ref_views(ref.seqs.size());
     for (size_t i = 0; i < ref.seqs.size(); i++) ref_views[i] = SeqView{ref.seqs[i].data(), (int64_t)ref.seqs[i].size()};
 
@@ -199,7 +222,28 @@ int main(int argc, char **argv)
             // D-SOFT for every read of the shard, both strands (darwin.cpp:209-288)
             auto td = Clock::now();
             std::vector<std::vector<uint64_t>> cand_f(nr), cand_r(nr);
-            {
+            if (sh.dsoft) {
+                // device-side filter: queries = (reads, k), (reverse-complemented reads, k) for every read of the shard
+                std::vector<int32_t> qsets(2 * nr);
+                std::vector<int64_t> qidx(2 * nr);
+                for (size_t k = 0; k < nr; k++) {
+                    qsets[2 * k] = GACT_SET_READS; qsets[2 * k + 1] = GACT_SET_READS_RC;
+                    qidx[2 * k] = qidx[2 * k + 1] = (int64_t)k;
+                }
+                std::vector<gact_dsoft_cand> cands(std::max<size_t>(1024, 8 * nr));
+                int64_t n_out = 0;
+                int rc = gact_dsoft_run(sh.dsoft, (int)(2 * nr), qsets.data(), qidx.data(), cands.data(), (int64_t)cands.size(), &n_out);
+                if (rc == GACT_ERR_NOMEM && n_out > (int64_t)cands.size()) {
+                    cands.resize((size_t)n_out);
+                    rc = gact_dsoft_run(sh.dsoft, (int)(2 * nr), qsets.data(), qidx.data(), cands.data(), (int64_t)cands.size(), &n_out);
+                }
+                if (rc) { sh.error = std::string("gact_dsoft_run: ") + gact_last_error(sh.eng); return; }
+                for (int64_t x = 0; x < n_out; x++) {
+                    const gact_dsoft_cand &c = cands[(size_t)x];
+                    auto &dst = (c.query & 1) ? cand_r[(size_t)(c.query >> 1)] : cand_f[(size_t)(c.query >> 1)];
+                    dst.push_back(((uint64_t)c.hit << 32) | c.offset);
+                }
+            } else {
                 std::vector<std::thread> th;
                 std::atomic<size_t> next(0);
                 for (int t = 0; t < sh.dsoft_threads; t++) th.emplace_back([&] {
@@ -289,8 +333,10 @@ int main(int argc, char **argv)
     const long align_ms = ms_since(t0);
     std::cout << "Time elapsed (seed table querying + aligning): " << align_ms << " msec" << std::endl;
     // GPU_close comes after the timed phase in the reference as well (darwin.cpp:634-642)
-    for (auto &sh : shards)
+    for (auto &sh : shards) {
+        if (sh.dsoft) { gact_dsoft_destroy(sh.dsoft); sh.dsoft = nullptr; }
         if (sh.eng) { gact_engine_destroy(sh.eng); sh.eng = nullptr; }
+    }
 
     int rcode = 0;
     uint64_t tiles = 0, cells = 0;

@@ -31,6 +31,15 @@ int dh_dsoft(void *t, const char *q, uint32_t qlen, int num_seeds, int threshold
     return n;
 }
 
+// raw tables of a SeedTable (to hand to gact_dsoft_create)
+void dh_seed_table_arrays(void *t, const uint32_t **index, uint64_t *index_entries, const uint32_t **pos, uint64_t *n_pos,
+                          uint32_t *max_occ)
+{
+    SeedTable *tab = (SeedTable *)t;
+    *index = tab->index_table(); *index_entries = tab->index_entries();
+    *pos = tab->pos_table(); *n_pos = tab->num_minimizers(); *max_occ = tab->kmer_max_occurence();
+}
+
 uint32_t dh_hash32(uint32_t key, int k) { return wang_hash32(key, k); }
 
 int dh_read_fasta(const char *path, char *names_out, int names_cap, long long *lens_out, int max_seqs)

@@ -41,6 +41,14 @@ public:
               int max_candidates, Scratch &s, std::vector<uint64_t> &candidates) const;
 
     uint32_t num_minimizers() const { return n_pos_; }
+    // raw tables, for the device-side filter (gact_dsoft_create)
+    const uint32_t *index_table() const { return index_table_; }
+    uint64_t index_entries() const { return ((uint64_t)1 << (2 * k_)) + 1; }
+    const uint32_t *pos_table() const { return pos_table_; }
+    uint32_t kmer_max_occurence() const { return kmer_max_occurence_; }
+    int kmer_size() const { return k_; }
+    int window_size() const { return w_; }
+    uint32_t bin_size() const { return bin_size_; }
 
 private:
     uint32_t ref_len_, bin_size_, log_bin_size_, kmer_max_occurence_;

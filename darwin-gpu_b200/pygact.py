@@ -53,7 +53,10 @@ EXPORTS = [
     "gact_engine_stage", "gact_engine_run_staged", "gact_engine_fetch_staged", "gact_engine_sync",
     "gact_engine_last_kernel_ms", "gact_engine_stats", "gact_engine_reset_stats",
     "gact_engine_set_kernel", "gact_engine_get_kernel", "gact_int_peak",
+    "gact_dsoft_create", "gact_dsoft_destroy", "gact_dsoft_run", "gact_dsoft_last_kernel_ms",
 ]
+
+DSOFT_CAND_DTYPE = np.dtype([("query", "<i4"), ("seq", "<i4"), ("hit", "<u4"), ("offset", "<u4")])
 
 _lib = None
 
@@ -116,6 +119,15 @@ def load():
     L.gact_engine_set_kernel.argtypes = [vp, i32]
     L.gact_engine_get_kernel.restype = i32
     L.gact_engine_get_kernel.argtypes = [vp]
+    L.gact_dsoft_create.restype = i32
+    L.gact_dsoft_create.argtypes = [C.POINTER(vp), vp, vp, C.c_uint64, vp, C.c_uint64, i32, i32, C.c_uint32,
+                                    C.c_uint32, i32, i32, i32]
+    L.gact_dsoft_destroy.restype = None
+    L.gact_dsoft_destroy.argtypes = [vp]
+    L.gact_dsoft_run.restype = i32
+    L.gact_dsoft_run.argtypes = [vp, i32, vp, vp, vp, i64, C.POINTER(i64)]
+    L.gact_dsoft_last_kernel_ms.restype = C.c_double
+    L.gact_dsoft_last_kernel_ms.argtypes = [vp]
     L.gact_int_peak.restype = i32
     L.gact_int_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
     _lib = L
@@ -290,3 +302,37 @@ def align_batch(engine, ref_seqs, query_seqs, reverses, firsts):
                 q += [int(res["max_i"][k]), int(res["max_j"][k])]
             out.append(q + unpack_states(st[k], int(res["n_states"][k])))
     return out
+
+
+class Dsoft:
+    """Device-side D-SOFT filter bound to an engine (seed table arrays come from the host builder)."""
+
+    def __init__(self, engine, index_ptr, index_entries, pos_ptr, n_pos, kmer_size=14, window_size=4, bin_size=64,
+                 max_occ=32, num_seeds=800, threshold=21, max_candidates=1000000):
+        self.eng = engine
+        self.h = C.c_void_p()
+        rc = engine.L.gact_dsoft_create(C.byref(self.h), engine.h, index_ptr, index_entries, pos_ptr, n_pos,
+                                        kmer_size, window_size, bin_size, max_occ, num_seeds, threshold, max_candidates)
+        engine._ck(rc, "gact_dsoft_create")
+
+    def run(self, sets, seq_index, cap=1 << 16):
+        sets = np.ascontiguousarray(sets, dtype=np.int32)
+        seq_index = np.ascontiguousarray(seq_index, dtype=np.int64)
+        while True:
+            out = np.zeros(cap, dtype=DSOFT_CAND_DTYPE)
+            n = C.c_int64(0)
+            rc = self.eng.L.gact_dsoft_run(self.h, len(sets), sets.ctypes.data, seq_index.ctypes.data,
+                                           out.ctypes.data, cap, C.byref(n))
+            if rc == -3 and n.value > cap:
+                cap = int(n.value)
+                continue
+            self.eng._ck(rc, "gact_dsoft_run")
+            return out[:n.value]
+
+    def last_kernel_ms(self):
+        return self.eng.L.gact_dsoft_last_kernel_ms(self.h)
+
+    def close(self):
+        if self.h:
+            self.eng.L.gact_dsoft_destroy(self.h)
+            self.h = None

@@ -198,6 +198,30 @@ int gact_engine_reset_stats(gact_engine *e);
 int gact_engine_set_kernel(gact_engine *e, int variant);
 int gact_engine_get_kernel(const gact_engine *e);
 
+/* ---- D-SOFT candidate filter on the device (seed_pos_table.cpp:100-167, ntcoding.cpp:155-182) ----
+ * The seed-position table (index_table_: 4^k + 1 entries, pos_table_) is built by the host
+ * (SeedPosTable constructor, seed_pos_table.cpp:46-98) and uploaded once; queries are sequences of
+ * the engine's uploaded sets.  Candidates come back grouped by query, in the reference's emission
+ * order: (hit << 32) | offset of the reference is {hit, offset} here. */
+typedef struct gact_dsoft gact_dsoft;
+typedef struct {
+    int32_t  query;     /* index into the queries passed to gact_dsoft_run               */
+    int32_t  seq;       /* emission order inside that query                              */
+    uint32_t hit;       /* position in the concatenated, bin-padded reference            */
+    uint32_t offset;    /* position in the query                                         */
+} gact_dsoft_cand;
+
+int  gact_dsoft_create(gact_dsoft **out, gact_engine *e, const uint32_t *index_table, uint64_t index_entries,
+                       const uint32_t *pos_table, uint64_t n_pos, int kmer_size, int window_size,
+                       uint32_t bin_size, uint32_t kmer_max_occurence, int num_seeds, int threshold,
+                       int max_candidates);
+void gact_dsoft_destroy(gact_dsoft *d);
+/* queries: (set, sequence index inside the set) pairs.  Returns GACT_ERR_NOMEM with *n_out set to the
+ * required capacity when out_cap is too small. */
+int  gact_dsoft_run(gact_dsoft *d, int n_queries, const int32_t *sets, const int64_t *seq_index,
+                    gact_dsoft_cand *out, int64_t out_cap, int64_t *n_out);
+double gact_dsoft_last_kernel_ms(const gact_dsoft *d);
+
 /* Integer/DPX issue-rate microbenchmark (the roofline denominator of the DP
  * kernels; MEASURED_PEAKS.json has none).  kind: 0 = IADD3, 1 = VIMNMX3.S32,
  * 2 = VIADDMNMX.S32, 3 = VIMNMX3.S16x2, 4 = VIADDMNMX.S16x2, 5 = LOP3,
