@@ -38,17 +38,18 @@ static void fail(gact_engine *e, const char *what, int rc)
     throw std::runtime_error(std::string(what) + ": " + gact_status_string(rc) + ": " + gact_last_error(e));
 }
 
+// OpenMP keeps a persistent worker pool: the loop runs a few hundred times per shard with a
+// body of ~100 us, so spawning std::threads per round would dominate
 template <class F>
 static void parallel_for(int threads, size_t n, F f)
 {
-    if (threads <= 1 || n < 256) { f(0, n); return; }
-    std::vector<std::thread> th;
-    const size_t T = (size_t)threads;
-    for (size_t t = 0; t < T; t++) {
-        const size_t a = n * t / T, b = n * (t + 1) / T;
-        if (a < b) th.emplace_back([=] { f(a, b); });
+    if (threads <= 1 || n < 512) { f(0, n); return; }
+    const long chunks = (long)std::min<size_t>((size_t)threads * 4, (n + 127) / 128);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+    for (long c = 0; c < chunks; c++) {
+        const size_t a = n * (size_t)c / (size_t)chunks, b = n * (size_t)(c + 1) / (size_t)chunks;
+        f(a, b);
     }
-    for (auto &x : th) x.join();
 }
 
 void GactScheduler::run(const std::vector<GactCall> &calls, std::vector<GactAlignment> &out, SchedulerStats *stats)
