@@ -44,6 +44,371 @@ struct DirWinH {
     }
 };
 
+// ---------------------------------------------------------------------------
+// Per-segment context and the building blocks shared by the tile kernel, the first-tile kernel and
+// the chain kernel.  Every function below is executed by the WHOLE warp (its shuffles and ballots use
+// the full mask); each 16-lane segment works on its own tile, segments without work pass n = m = 0.
+template <int CS, int LANES>
+struct SegCtx {
+    static constexpr int TS = CS * 2 * LANES;
+    int lane, seg, sl, segbase;
+    uint32_t *rr;            // rr[i]: substitution table of R[i] (LUT) or enc(R[i]) | enc(R[i-1]) << 16
+    uint16_t *qs, *rb;       // enc(Q[j]), enc(R[i])
+    void *dirbase;
+    // constants of the biased x16 domain
+    int B, KO, KI, KD, ONE, et, match, mismatch, gap_open, gap_extend;
+    uint32_t Bp, ma16, mi16, ge16, borderD_tag, borderD_raw, lut_mis, lut_delta;
+
+    __device__ __forceinline__ void init(const KParams &P, uint8_t *smem, int warp, size_t seq_bytes, uint8_t *gscratch,
+                                         size_t dir_bytes, int global_warp)
+    {
+        asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+        seg = lane / LANES; sl = lane % LANES; segbase = seg * LANES;
+        constexpr int TPW = 32 / LANES;
+        uint8_t *my = smem + ((size_t)warp * TPW + seg) * seq_bytes;
+        rr = reinterpret_cast<uint32_t *>(my);
+        qs = reinterpret_cast<uint16_t *>(my + (TS + 2) * 4);
+        rb = reinterpret_cast<uint16_t *>(my + (TS + 2) * 6);
+        dirbase = gscratch ? (void *)(gscratch + ((size_t)global_warp * TPW + seg) * dir_bytes) : nullptr;
+        B = P.s16_bias; Bp = pk16(B);
+        match = P.match; mismatch = P.mismatch; gap_open = P.gap_open; gap_extend = P.gap_extend; et = P.et;
+        ma16 = pk16(P.match * 16); mi16 = pk16(P.mismatch * 16); ge16 = pk16(P.gap_extend * 16);
+        KO = (P.gap_open * 16) * 65537;
+        KI = (P.gap_open * 16 - 5) * 65537;
+        KD = (P.gap_open * 16 - 10) * 65537;
+        ONE = P.one;
+        borderD_tag = ((uint32_t)(B + P.gap_open * 16 + 5) << 16) | (uint32_t)B;
+        borderD_raw = ((uint32_t)(B + P.gap_open * 16) << 16) | (uint32_t)B;
+        lut_mis = (uint32_t)((P.mismatch * 16) & 0xff) * 0x01010101u;
+        lut_delta = (uint32_t)(((P.match ^ P.mismatch) * 16) & 0xff);
+    }
+};
+
+// stage the tile's bases (DP order) into the segment's shared-memory arrays
+template <int CS, int LANES, bool LUT>
+__device__ __forceinline__ void seg_stage(const SegCtx<CS, LANES> &cx, const SeqSetDev &rset, const SeqSetDev &qset,
+                                          long long ref_off, int ref_len, long long query_off, int query_len,
+                                          int reverse, int n, int m)
+{
+    __syncwarp();
+    if (n > 0 && m > 0) {
+        for (int x = cx.sl; x <= n + 1; x += LANES) {
+            const bool in = (x >= 1 && x <= n);
+            const int base = in ? tile_base(rset, ref_off, ref_len, reverse, x) : 0;
+            cx.rb[x] = (uint16_t)(in ? enc_base(base) : SENT_R);
+            if (LUT) {
+                const int code = (base == 'A') ? 0 : (base == 'C') ? 1 : (base == 'G') ? 2 : (base == 'T') ? 3 : 4;
+                uint32_t w = cx.lut_mis;
+                if (in && code < 4) w ^= cx.lut_delta << (8 * code);
+                cx.rr[x] = w;
+            }
+        }
+        for (int x = cx.sl; x <= m; x += LANES)
+            cx.qs[x] = (x >= 1) ? (uint16_t)enc_base(tile_base(qset, query_off, query_len, reverse, x)) : (uint16_t)SENT_Q;
+    }
+    __syncwarp();
+    if (!LUT && n > 0 && m > 0) {
+        for (int x = cx.sl; x <= n + 1; x += LANES)
+            cx.rr[x] = (uint32_t)cx.rb[x] | ((uint32_t)(x >= 1 ? cx.rb[x - 1] : (uint16_t)SENT_R) << 16);
+    }
+    __syncwarp();
+}
+
+// per-lane query registers: enc pairs (general) or PRMT selectors (LUT)
+template <int CS, int LANES, bool LUT>
+__device__ __forceinline__ void seg_load_q(const SegCtx<CS, LANES> &cx, int m, uint32_t (&q)[CS])
+{
+#pragma unroll
+    for (int c = 0; c < CS; c++) {
+        const int jl = (2 * cx.sl) * CS + c + 1, jh = (2 * cx.sl + 1) * CS + c + 1;
+        const uint32_t el = jl <= m ? (uint32_t)cx.qs[jl] : SENT_Q + c, eh = jh <= m ? (uint32_t)cx.qs[jh] : SENT_Q + c;
+        if (LUT) {
+            const uint32_t tl = (el >> 1) & 3u, th = (eh >> 1) & 3u;       // A0 C1 G3 T2 -> 0 1 2 3 below
+            const uint32_t l2 = (jl <= m) ? (tl ^ (tl >> 1)) : 0u, h2 = (jh <= m) ? (th ^ (th >> 1)) : 0u;
+            q[c] = l2 | ((8u | l2) << 4) | ((4u | h2) << 8) | ((12u | h2) << 12);
+        } else {
+            q[c] = el | (eh << 16);
+        }
+    }
+}
+
+// DP of one tile per segment: fills the direction window, returns the corner score H[n][m]
+template <int CS, int LANES, bool LUT>
+__device__ __forceinline__ int seg_dp(const SegCtx<CS, LANES> &cx, const uint32_t (&q)[CS], int n, int m,
+                                      const DirWinH<CS> &dw)
+{
+    constexpr int NW = DirWinH<CS>::NW;
+    constexpr int R = DirWinH<CS>::R;
+    const int sl = cx.sl, B = cx.B;
+    const uint32_t Bp = cx.Bp, ge16 = cx.ge16;
+    const int laststrip = (m > 0) ? (m - 1) / CS : -1;
+    const int lastlane = laststrip >> 1;                       // segment-local
+    const int c_lane = max(lastlane, 0), c_half = laststrip & 1, c_col = (m > 0) ? (m - 1) - laststrip * CS : 0;
+    const int kc = n + 2 * c_lane + c_half;
+    const bool work = (n > 0 && m > 0);
+    const int steps_seg = work ? n + 1 + 2 * lastlane : 0;
+    // the first lane that keeps direction codes (lane0) reaches window row i0 at step i0 + 2*lane0;
+    // until then every lane can stay in the cheaper untagged loop
+    int steps = steps_seg, k1 = work ? min(dw.i0 - 1 + 2 * dw.lane0, steps_seg) : 0x3fffffff;
+#pragma unroll
+    for (int o = LANES; o < 32; o <<= 1) {
+        steps = max(steps, __shfl_xor_sync(FULL, steps, o));
+        k1 = min(k1, __shfl_xor_sync(FULL, k1, o));
+    }
+    k1 = min(k1, steps);
+    const int kfirst = (work && sl <= lastlane) ? 2 * sl + 1 : 0x3fffffff;
+    const int kstore = (work && sl >= dw.lane0) ? dw.i0 + 2 * sl : 0x3fffffff;
+    const uint32_t *rrp = cx.rr - 2 * sl;               // rrp[k] = rr[k - 2*sl]
+
+    // ---------------- phase 1: rows above every segment's window, score only ----------------
+    uint32_t Gup[CS], IoUp[CS], IcUp[CS];
+#pragma unroll
+    for (int c = 0; c < CS; c++) {
+        Gup[c] = Bp;
+        IoUp[c] = pk16(B + cx.gap_open * 16, S16_NEG);
+        IcUp[c] = pk16(S16_NEG, S16_NEG);
+    }
+    uint32_t eG = Bp, eD = pk16(S16_NEG), diag = Bp;
+    int k = 1;
+    for (; k <= k1; k++) {
+        const uint32_t pack = __byte_perm(eG, eD, 0x7632);
+        uint32_t recv = __shfl_up_sync(FULL, pack, 1, LANES);
+        if (sl == 0) recv = cx.borderD_raw;
+        const uint32_t inG = __byte_perm(recv, eG, 0x5410);
+        const uint32_t inD = __byte_perm(recv, eD, 0x5432);
+        if ((unsigned)(k - kfirst) <= (unsigned)n) {
+            const uint32_t rlo = rrp[k], rhi = LUT ? rrp[k - 1] : 0u;
+            uint32_t hd = diag, dv = inD;
+#pragma unroll
+            for (int c = 0; c < CS; c++) {
+                const uint32_t sc = subst_score<LUT>(q[c], rlo, rhi, cx.ma16, cx.mi16);
+                const uint32_t mc = __viaddmax_s16x2(hd, sc, Bp);
+                hd = Gup[c];
+                const uint32_t iv = __viaddmax_s16x2(IcUp[c], ge16, IoUp[c]);
+                Gup[c] = __vimax3_s16x2(mc, iv, dv);
+                const uint32_t mo = (uint32_t)((int)mc * cx.ONE + cx.KO);
+                IoUp[c] = mo;
+                IcUp[c] = iv;
+                dv = __viaddmax_s16x2(dv, ge16, mo);
+            }
+            eG = Gup[CS - 1];
+            eD = dv;
+            diag = inG;
+        }
+    }
+    // ---------------- switch to the tagged domain ----------------
+#pragma unroll
+    for (int c = 0; c < CS; c++) {
+        IoUp[c] = __vadd2(IoUp[c], pk16(10));
+        IcUp[c] = __vadd2(IcUp[c], pk16(8));
+    }
+    eD = __vadd2(eD, pk16(4));
+
+    // ---------------- phase 2: window rows, tagged values + direction codes ----------------
+    uint32_t *wptr = dw.w + ((k - 2 * sl - dw.i0) * dw.nl + (sl - dw.lane0)) * NW;
+    uint16_t *hptr = dw.h + ((k - 2 * sl - dw.i0) * dw.nl + (sl - dw.lane0));
+    int corner16 = B;
+    for (; k <= steps; k++) {
+        const uint32_t pack = __byte_perm(eG, eD, 0x7632);
+        uint32_t recv = __shfl_up_sync(FULL, pack, 1, LANES);
+        if (sl == 0) recv = cx.borderD_tag;
+        const uint32_t inG = __byte_perm(recv, eG, 0x5410);
+        const uint32_t inD = __byte_perm(recv, eD, 0x5432);
+        if ((unsigned)(k - kfirst) <= (unsigned)n) {
+            const uint32_t rlo = rrp[k], rhi = LUT ? rrp[k - 1] : 0u;
+            uint32_t hd = diag, dv = inD;
+            uint32_t acc[NW + 1];
+#pragma unroll
+            for (int c = 0; c < CS; c++) {
+                const uint32_t sc = subst_score<LUT>(q[c], rlo, rhi, cx.ma16, cx.mi16);
+                const uint32_t mt = __viaddmax_s16x2(hd, sc, Bp) | 0x000f000fu;
+                hd = Gup[c];
+                const uint32_t iv = __viaddmax_s16x2(IcUp[c], ge16, IoUp[c]);
+                const uint32_t g = __vimax3_s16x2(mt, iv, dv);
+                const uint32_t code = (g & 0x000c000cu) | ((iv | dv) & 0x00030003u);
+                if ((c & 3) == 0) acc[c >> 2] = code; else acc[c >> 2] = acc[c >> 2] * 16u + code;
+                Gup[c] = g;
+                IoUp[c] = (uint32_t)((int)mt * cx.ONE + cx.KI);
+                IcUp[c] = iv & 0xfffdfffdu;
+                dv = __viaddmax_s16x2(dv & 0xfffefffeu, ge16, (uint32_t)((int)mt * cx.ONE + cx.KD));
+            }
+            eG = Gup[CS - 1];
+            eD = dv;
+            diag = inG;
+            if (k >= kstore) {
+#pragma unroll
+                for (int x = 0; x < NW; x++) wptr[x] = acc[x];
+                if (R) *hptr = (uint16_t)((acc[NW] & 0xffu) | ((acc[NW] >> 8) & 0xff00u));
+            }
+            if (k == kc) {
+                uint32_t gsel = 0;
+#pragma unroll
+                for (int c = 0; c < CS; c++) if (c == c_col) gsel = Gup[c];
+                corner16 = (int)(short)(c_half ? (gsel >> 16) : (gsel & 0xffffu));
+            }
+        }
+        wptr += dw.nl * NW;
+        hptr += dw.nl;
+    }
+    int corner = (__shfl_sync(FULL, corner16, cx.segbase + c_lane) - B) >> 4;
+    if (!work) corner = 0;
+    __threadfence_block();
+    __syncwarp();
+    return corner;
+}
+
+// Result of one traceback (align.cpp:185-230), all lanes of the segment hold the same values.
+struct SegTrace {
+    int cnt;             // number of states
+    int is, js;          // reference / query bases consumed
+    int col_score;       // sum of the per-column scores of gact.cpp:197-210 over these states
+    int first_gap;       // was the first state a gap column (valid if cnt > 0)
+    int last_gap;        // prev_gap after the last state
+};
+
+// Traceback by the segment.  EMIT: write the states (one byte each) into stbuf.  prev_gap: whether the
+// column scored just before this tile's first state was a gap column (for the open/extend accounting).
+// In state M the lanes inspect the next LANES cells down the diagonal at once; ballot + popc give the
+// scores along the run, ffs its length.
+template <int CS, int LANES, bool EMIT>
+__device__ __forceinline__ SegTrace seg_traceback(const SegCtx<CS, LANES> &cx, const DirWinH<CS> &dw, int n, int m,
+                                                  int corner, uint8_t *stbuf, int prev_gap)
+{
+    constexpr unsigned SEGMASK = (LANES == 32) ? 0xffffffffu : ((1u << LANES) - 1u);
+    const int sl = cx.sl, et = cx.et;
+    const int ma = cx.match, mi = cx.mismatch, go = cx.gap_open, ge = cx.gap_extend;
+    const bool work = (n > 0 && m > 0);
+    const int i0 = dw.i0, j0 = max(m - et, 1);
+    int i = n, j = m, cnt = 0, v = corner, ri = et, rj = et;
+    int col = 0, first_gap = 0, pg = prev_gap;
+    int state = (work && v > 0) ? (dw.load(i, j) >> 2) : 0;
+    bool act = (state != 0);
+    while (__any_sync(FULL, act)) {
+        const bool inM = act && state == 3;
+        const int it = i - sl, jt = j - sl;
+        const bool inb = inM && it >= i0 && jt >= j0;
+        const int code_t = inb ? dw.load(it, jt) : 0;
+        const bool match_t = inb && (cx.rb[it] == cx.qs[jt]);
+        const unsigned mm = (__ballot_sync(FULL, match_t) >> cx.segbase) & SEGMASK;
+        const int below = __popc(mm & ((1u << sl) - 1u));
+        const int v_t = v - (below * ma + (sl - below) * mi);
+        const bool isM_t = (sl == 0) || (inb && v_t > 0 && (code_t >> 2) == 3);
+        const unsigned run = (__ballot_sync(FULL, isM_t) >> cx.segbase) & SEGMASK;
+        int L = __ffs(~run) - 1;
+        if (L < 0 || L > LANES - 1) L = LANES - 1;
+        L = min(L, min(ri, rj));
+        const int codeL = __shfl_sync(FULL, code_t, cx.segbase + L);
+        if (inM) {
+            if (EMIT && sl < L) stbuf[cnt + sl] = 3;
+            const int bl = __popc(mm & ((1u << L) - 1u));
+            const int d = bl * ma + (L - bl) * mi;
+            cnt += L; ri -= L; rj -= L;
+            v -= d; col += d;
+            if (L > 0) pg = 0;
+            i -= L; j -= L;
+            state = (i >= i0 && j >= j0 && v > 0) ? (codeL >> 2) : 0;
+        } else if (act) {
+            const int code = dw.load(i, j);
+            const bool open = (state == 2) ? (code & 2) : (code & 1);
+            if (EMIT && sl == 0) stbuf[cnt] = (uint8_t)state;
+            if (cnt == 0) first_gap = 1;
+            cnt++;
+            v -= open ? go : ge;
+            col += pg ? ge : go;
+            pg = 1;
+            if (state == 2) { i--; ri--; } else { j--; rj--; }
+            state = open ? 3 : state;
+            if (i <= 0 || j <= 0) state = 0;
+        }
+        act = (state != 0 && ri > 0 && rj > 0);
+    }
+    __syncwarp();
+    SegTrace t;
+    t.cnt = cnt; t.is = et - ri; t.js = et - rj; t.col_score = col; t.first_gap = first_gap; t.last_gap = pg;
+    return t;
+}
+
+// First-tile pass (align.cpp:173-177,190): score only + position of the LAST maximum in (i outer, j inner)
+// order.  Per column and half-word the running maximum and the row where it was last reached are kept
+// (VIMNMX.S16x2 with predicate outputs = the reference's `>=` update); columns are compared by (H, i, j).
+template <int CS, int LANES, bool LUT>
+__device__ __forceinline__ void seg_first_pass(const SegCtx<CS, LANES> &cx, const uint32_t (&q)[CS], int n, int m,
+                                               int *max_i, int *max_j)
+{
+    const int sl = cx.sl, B = cx.B;
+    const uint32_t Bp = cx.Bp, ge16 = cx.ge16;
+    const bool work = (n > 0 && m > 0);
+    const int laststrip = (m > 0) ? (m - 1) / CS : -1;
+    const int lastlane = laststrip >> 1;
+    int steps = work ? n + 1 + 2 * lastlane : 0;
+#pragma unroll
+    for (int o = LANES; o < 32; o <<= 1) steps = max(steps, __shfl_xor_sync(FULL, steps, o));
+    const int kfirst = (work && sl <= lastlane) ? 2 * sl + 1 : 0x3fffffff;
+    const uint32_t *rrp = cx.rr - 2 * sl;
+
+    uint32_t Gup[CS], IoUp[CS], IcUp[CS], best[CS], brow[CS];
+#pragma unroll
+    for (int c = 0; c < CS; c++) {
+        Gup[c] = Bp;
+        IoUp[c] = pk16(B + cx.gap_open * 16, S16_NEG);
+        IcUp[c] = pk16(S16_NEG, S16_NEG);
+        best[c] = 0;                               // below every H (H >= B > 0): the first valid cell always updates
+        brow[c] = 0;
+    }
+    uint32_t eG = Bp, eD = pk16(S16_NEG), diag = Bp;
+    for (int k = 1; k <= steps; k++) {
+        const uint32_t pack = __byte_perm(eG, eD, 0x7632);
+        uint32_t recv = __shfl_up_sync(FULL, pack, 1, LANES);
+        if (sl == 0) recv = cx.borderD_raw;
+        const uint32_t inG = __byte_perm(recv, eG, 0x5410);
+        const uint32_t inD = __byte_perm(recv, eD, 0x5432);
+        const int ilo = k - 2 * sl;
+        if ((unsigned)(k - kfirst) <= (unsigned)n) {
+            const uint32_t rlo = rrp[k], rhi = LUT ? rrp[k - 1] : 0u;
+            // rows that do not exist (low half: row n+1, high half: row 0) must not be recorded
+            const uint32_t keep = ((ilo <= n) ? 0x0000ffffu : 0u) | ((ilo >= 2) ? 0xffff0000u : 0u);
+            const uint32_t ipair = pk16(ilo, ilo - 1);
+            uint32_t hd = diag, dv = inD;
+#pragma unroll
+            for (int c = 0; c < CS; c++) {
+                const uint32_t sc = subst_score<LUT>(q[c], rlo, rhi, cx.ma16, cx.mi16);
+                const uint32_t mc = __viaddmax_s16x2(hd, sc, Bp);
+                hd = Gup[c];
+                const uint32_t iv = __viaddmax_s16x2(IcUp[c], ge16, IoUp[c]);
+                const uint32_t h = __vimax3_s16x2(mc, iv, dv);
+                Gup[c] = h;
+                const uint32_t mo = (uint32_t)((int)mc * cx.ONE + cx.KO);
+                IoUp[c] = mo;
+                IcUp[c] = iv;
+                dv = __viaddmax_s16x2(dv, ge16, mo);
+                bool ph, pl;
+                best[c] = __vibmax_s16x2(h & keep, best[c], &ph, &pl);      // pred = (h >= best): last maximum wins
+                if (pl) brow[c] = __byte_perm(brow[c], ipair, 0x3254);
+                if (ph) brow[c] = __byte_perm(brow[c], ipair, 0x7610);
+            }
+            eG = Gup[CS - 1];
+            eD = dv;
+            diag = inG;
+        }
+    }
+    // best cell of this lane by (H, i, j); i, j <= 320 take 9 bits each here
+    int key = -1;
+#pragma unroll
+    for (int c = 0; c < CS; c++) {
+        const int jl = (2 * sl) * CS + c + 1, jh = (2 * sl + 1) * CS + c + 1;
+        const int hl = (int)(best[c] & 0xffffu), hh = (int)(best[c] >> 16);
+        const int il = (int)(brow[c] & 0xffffu), ih = (int)(brow[c] >> 16);
+        if (work && jl <= m && il >= 1) key = max(key, (((hl - B) >> 4) << 18) | (il << 9) | jl);
+        if (work && jh <= m && ih >= 1) key = max(key, (((hh - B) >> 4) << 18) | (ih << 9) | jh);
+    }
+#pragma unroll
+    for (int o = 1; o < LANES; o <<= 1) key = max(key, __shfl_xor_sync(FULL, key, o));
+    if (key < 0) { *max_i = 0; *max_j = 0; }
+    else { *max_j = key & 511; *max_i = (key >> 9) & 511; }
+}
+
+// ---------------------------------------------------------------------------
+// tile kernel: one tile per segment, results + packed states to global memory
 template <int CS, int LANES, bool LUT>
 __global__ void __launch_bounds__(128, 4)
 gact_tile_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *__restrict__ descs,
@@ -52,36 +417,10 @@ gact_tile_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *_
                       int pitch_words, int *counter, size_t seq_bytes, uint8_t *gscratch, size_t dir_bytes)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int TPW = 32 / LANES;                   // tiles per warp
-    constexpr int TS = CS * 2 * LANES;
-    constexpr int NW = DirWinH<CS>::NW;
-    constexpr int R = DirWinH<CS>::R;
-    constexpr unsigned SEGMASK = (LANES == 32) ? 0xffffffffu : ((1u << LANES) - 1u);
-    int lane;
-    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
-    const int warp = threadIdx.x >> 5;
-    const int seg = lane / LANES, sl = lane % LANES;
-    const int segbase = seg * LANES;
-
-    // per-segment carve-out: rr[TS+2] words | qs[TS+2] halves | rb[TS+2] halves
-    uint8_t *my = smem + ((size_t)warp * TPW + seg) * seq_bytes;
-    uint32_t *rr = reinterpret_cast<uint32_t *>(my);
-    uint16_t *qs = reinterpret_cast<uint16_t *>(my + (TS + 2) * 4);
-    uint16_t *rb = reinterpret_cast<uint16_t *>(my + (TS + 2) * 6);
-    void *dirbase = gscratch + (((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * TPW + seg) * dir_bytes;
-
-    const int B = P.s16_bias;
-    const uint32_t Bp = pk16(B);
-    const uint32_t ma16 = pk16(P.match * 16), mi16 = pk16(P.mismatch * 16);
-    const uint32_t ge16 = pk16(P.gap_extend * 16);
-    const int KO = (P.gap_open * 16) * 65537;
-    const int KI = (P.gap_open * 16 - 5) * 65537;
-    const int KD = (P.gap_open * 16 - 10) * 65537;
-    const int ONE = P.one;
-    const uint32_t borderD_tag = ((uint32_t)(B + P.gap_open * 16 + 5) << 16) | (uint32_t)B;
-    const uint32_t borderD_raw = ((uint32_t)(B + P.gap_open * 16) << 16) | (uint32_t)B;
-    const uint32_t lut_mis = (uint32_t)((P.mismatch * 16) & 0xff) * 0x01010101u;
-    const int et = P.et;
+    constexpr int TPW = 32 / LANES;
+    SegCtx<CS, LANES> cx;
+    cx.init(P, smem, threadIdx.x >> 5, seq_bytes, gscratch, dir_bytes, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+    const int lane = cx.lane, seg = cx.seg, sl = cx.sl;
 
     for (;;) {
         int t0 = 0;
@@ -96,240 +435,44 @@ gact_tile_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *_
         if (valid) d = descs[t];
         int n = d.ref_len, m = d.query_len;
         if (valid && d.first) { n = eff[t].n; m = eff[t].m; }
-        const SeqSetDev &rset = P.sets[d.ref_set];
-        const SeqSetDev &qset = P.sets[d.query_set];
 
-        __syncwarp();
-        if (n > 0 && m > 0) {
-            for (int x = sl; x <= n + 1; x += LANES) {
-                const bool in = (x >= 1 && x <= n);
-                const int base = in ? tile_base(rset, d.ref_off, d.ref_len, d.reverse, x) : 0;
-                rb[x] = (uint16_t)(in ? enc_base(base) : SENT_R);
-                if (LUT) {
-                    const int code = (base == 'A') ? 0 : (base == 'C') ? 1 : (base == 'G') ? 2 : (base == 'T') ? 3 : 4;
-                    uint32_t w = lut_mis;
-                    if (in && code < 4) w ^= (uint32_t)(((P.match ^ P.mismatch) * 16) & 0xff) << (8 * code);
-                    rr[x] = w;
-                }
-            }
-            for (int x = sl; x <= m; x += LANES)
-                qs[x] = (x >= 1) ? (uint16_t)enc_base(tile_base(qset, d.query_off, d.query_len, d.reverse, x)) : (uint16_t)SENT_Q;
-        }
-        __syncwarp();
-        if (!LUT && n > 0 && m > 0) {
-            for (int x = sl; x <= n + 1; x += LANES)
-                rr[x] = (uint32_t)rb[x] | ((uint32_t)(x >= 1 ? rb[x - 1] : (uint16_t)SENT_R) << 16);
-        }
-        __syncwarp();
-
+        seg_stage<CS, LANES, LUT>(cx, P.sets[d.ref_set], P.sets[d.query_set], d.ref_off, d.ref_len, d.query_off,
+                                  d.query_len, d.reverse, n, m);
         uint32_t q[CS];
-#pragma unroll
-        for (int c = 0; c < CS; c++) {
-            const int jl = (2 * sl) * CS + c + 1, jh = (2 * sl + 1) * CS + c + 1;
-            const uint32_t el = jl <= m ? (uint32_t)qs[jl] : SENT_Q + c, eh = jh <= m ? (uint32_t)qs[jh] : SENT_Q + c;
-            if (LUT) {
-                const uint32_t tl = (el >> 1) & 3u, th = (eh >> 1) & 3u;       // A0 C1 G3 T2 -> 0 1 2 3 below
-                const uint32_t l2 = (jl <= m) ? (tl ^ (tl >> 1)) : 0u, h2 = (jh <= m) ? (th ^ (th >> 1)) : 0u;
-                q[c] = l2 | ((8u | l2) << 4) | ((4u | h2) << 8) | ((12u | h2) << 12);
-            } else {
-                q[c] = el | (eh << 16);
-            }
-        }
-
+        seg_load_q<CS, LANES, LUT>(cx, m, q);
         DirWinH<CS> dw;
-        dw.init(dirbase, n, m, P);
-        const int laststrip = (m > 0) ? (m - 1) / CS : -1;
-        const int lastlane = laststrip >> 1;                       // segment-local
-        const int c_lane = max(lastlane, 0), c_half = laststrip & 1, c_col = (m > 0) ? (m - 1) - laststrip * CS : 0;
-        const int kc = n + 2 * c_lane + c_half;
-        const bool work = (n > 0 && m > 0);
-        const int steps_seg = work ? n + 1 + 2 * lastlane : 0;
-        // the first lane that keeps direction codes (lane0) reaches window row i0 at step i0 + 2*lane0;
-        // until then every lane can stay in the cheaper untagged loop
-        int steps = steps_seg, k1 = work ? min(dw.i0 - 1 + 2 * dw.lane0, steps_seg) : 0x3fffffff;
+        dw.init(cx.dirbase, n, m, P);
+        const int corner = seg_dp<CS, LANES, LUT>(cx, q, n, m, dw);
+        uint8_t *stbuf = reinterpret_cast<uint8_t *>(cx.rr);      // rr[] is dead after the DP
+        const SegTrace tr = seg_traceback<CS, LANES, true>(cx, dw, n, m, corner, stbuf, 0);
+        if (valid) {
+            uint32_t *out = states + (size_t)t * pitch_words;
+            for (int w = sl; w * 16 < tr.cnt; w += LANES) {
+                uint32_t a = 0;
 #pragma unroll
-        for (int o = LANES; o < 32; o <<= 1) {
-            steps = max(steps, __shfl_xor_sync(FULL, steps, o));
-            k1 = min(k1, __shfl_xor_sync(FULL, k1, o));
-        }
-        k1 = min(k1, steps);
-        const int kfirst = (work && sl <= lastlane) ? 2 * sl + 1 : 0x3fffffff;
-        const int kstore = (work && sl >= dw.lane0) ? dw.i0 + 2 * sl : 0x3fffffff;
-        const uint32_t *rrp = rr - 2 * sl;               // rrp[k] = rr[k - 2*sl]
-
-        // ---------------- phase 1: rows above every segment's window, score only ----------------
-        uint32_t Gup[CS], IoUp[CS], IcUp[CS];
-#pragma unroll
-        for (int c = 0; c < CS; c++) {
-            Gup[c] = Bp;
-            IoUp[c] = pk16(B + P.gap_open * 16, S16_NEG);
-            IcUp[c] = pk16(S16_NEG, S16_NEG);
-        }
-        uint32_t eG = Bp, eD = pk16(S16_NEG), diag = Bp;
-        int k = 1;
-        for (; k <= k1; k++) {
-            const uint32_t pack = __byte_perm(eG, eD, 0x7632);
-            uint32_t recv = __shfl_up_sync(FULL, pack, 1, LANES);
-            if (sl == 0) recv = borderD_raw;
-            const uint32_t inG = __byte_perm(recv, eG, 0x5410);
-            const uint32_t inD = __byte_perm(recv, eD, 0x5432);
-            if ((unsigned)(k - kfirst) <= (unsigned)n) {
-                const uint32_t rlo = rrp[k], rhi = LUT ? rrp[k - 1] : 0u;
-                uint32_t hd = diag, dv = inD;
-#pragma unroll
-                for (int c = 0; c < CS; c++) {
-                    const uint32_t sc = subst_score<LUT>(q[c], rlo, rhi, ma16, mi16);
-                    const uint32_t mc = __viaddmax_s16x2(hd, sc, Bp);
-                    hd = Gup[c];
-                    const uint32_t iv = __viaddmax_s16x2(IcUp[c], ge16, IoUp[c]);
-                    Gup[c] = __vimax3_s16x2(mc, iv, dv);
-                    const uint32_t mo = (uint32_t)((int)mc * ONE + KO);
-                    IoUp[c] = mo;
-                    IcUp[c] = iv;
-                    dv = __viaddmax_s16x2(dv, ge16, mo);
+                for (int x = 0; x < 16; x++) {
+                    const int idx = w * 16 + x;
+                    const uint32_t st = (idx < tr.cnt) ? stbuf[idx] : 0u;
+                    a |= st << (2 * x);
                 }
-                eG = Gup[CS - 1];
-                eD = dv;
-                diag = inG;
+                out[w] = a;
             }
-        }
-        // ---------------- switch to the tagged domain ----------------
-#pragma unroll
-        for (int c = 0; c < CS; c++) {
-            IoUp[c] = __vadd2(IoUp[c], pk16(10));
-            IcUp[c] = __vadd2(IcUp[c], pk16(8));
-        }
-        eD = __vadd2(eD, pk16(4));
-
-        // ---------------- phase 2: window rows, tagged values + direction codes ----------------
-        uint32_t *wptr = dw.w + ((k - 2 * sl - dw.i0) * dw.nl + (sl - dw.lane0)) * NW;
-        uint16_t *hptr = dw.h + ((k - 2 * sl - dw.i0) * dw.nl + (sl - dw.lane0));
-        int corner16 = B;
-        for (; k <= steps; k++) {
-            const uint32_t pack = __byte_perm(eG, eD, 0x7632);
-            uint32_t recv = __shfl_up_sync(FULL, pack, 1, LANES);
-            if (sl == 0) recv = borderD_tag;
-            const uint32_t inG = __byte_perm(recv, eG, 0x5410);
-            const uint32_t inD = __byte_perm(recv, eD, 0x5432);
-            if ((unsigned)(k - kfirst) <= (unsigned)n) {
-                const uint32_t rlo = rrp[k], rhi = LUT ? rrp[k - 1] : 0u;
-                uint32_t hd = diag, dv = inD;
-                uint32_t acc[NW + 1];
-#pragma unroll
-                for (int c = 0; c < CS; c++) {
-                    const uint32_t sc = subst_score<LUT>(q[c], rlo, rhi, ma16, mi16);
-                    const uint32_t mt = __viaddmax_s16x2(hd, sc, Bp) | 0x000f000fu;
-                    hd = Gup[c];
-                    const uint32_t iv = __viaddmax_s16x2(IcUp[c], ge16, IoUp[c]);
-                    const uint32_t g = __vimax3_s16x2(mt, iv, dv);
-                    const uint32_t code = (g & 0x000c000cu) | ((iv | dv) & 0x00030003u);
-                    if ((c & 3) == 0) acc[c >> 2] = code; else acc[c >> 2] = acc[c >> 2] * 16u + code;
-                    Gup[c] = g;
-                    IoUp[c] = (uint32_t)((int)mt * ONE + KI);
-                    IcUp[c] = iv & 0xfffdfffdu;
-                    dv = __viaddmax_s16x2(dv & 0xfffefffeu, ge16, (uint32_t)((int)mt * ONE + KD));
-                }
-                eG = Gup[CS - 1];
-                eD = dv;
-                diag = inG;
-                if (k >= kstore) {
-#pragma unroll
-                    for (int x = 0; x < NW; x++) wptr[x] = acc[x];
-                    if (R) *hptr = (uint16_t)((acc[NW] & 0xffu) | ((acc[NW] >> 8) & 0xff00u));
-                }
-                if (k == kc) {
-                    uint32_t gsel = 0;
-#pragma unroll
-                    for (int c = 0; c < CS; c++) if (c == c_col) gsel = Gup[c];
-                    corner16 = (int)(short)(c_half ? (gsel >> 16) : (gsel & 0xffffu));
-                }
-            }
-            wptr += dw.nl * NW;
-            hptr += dw.nl;
-        }
-        int corner = (__shfl_sync(FULL, corner16, segbase + c_lane) - B) >> 4;
-        if (!work) corner = 0;
-        __threadfence_block();
-        __syncwarp();
-
-        // ---------------- traceback, align.cpp:185-230, LANES lanes per tile ----------------
-        // (see traceback_tile16 in gact_kernels_s16.cuh; here both segments run side by side, so the
-        //  M-run evaluation is executed by every lane and only applied where the segment is in state M)
-        {
-            uint8_t *stbuf = reinterpret_cast<uint8_t *>(rr);      // rr[] is dead now
-            const int ma = P.match, mi = P.mismatch, go = P.gap_open, ge = P.gap_extend;
-            const int i0 = dw.i0, j0 = max(m - et, 1);
-            int i = n, j = m, cnt = 0, v = corner, ri = et, rj = et;
-            int state = (work && v > 0) ? (dw.load(i, j) >> 2) : 0;
-            bool act = (state != 0);
-            while (__any_sync(FULL, act)) {
-                const bool inM = act && state == 3;
-                const int it = i - sl, jt = j - sl;
-                const bool inb = inM && it >= i0 && jt >= j0;
-                const int code_t = inb ? dw.load(it, jt) : 0;
-                const bool match_t = inb && (rb[it] == qs[jt]);
-                const unsigned mm = (__ballot_sync(FULL, match_t) >> segbase) & SEGMASK;
-                const int below = __popc(mm & ((1u << sl) - 1u));
-                const int v_t = v - (below * ma + (sl - below) * mi);
-                const bool isM_t = (sl == 0) || (inb && v_t > 0 && (code_t >> 2) == 3);
-                const unsigned run = (__ballot_sync(FULL, isM_t) >> segbase) & SEGMASK;
-                int L = __ffs(~run) - 1;
-                if (L < 0 || L > LANES - 1) L = LANES - 1;
-                L = min(L, min(ri, rj));
-                const int codeL = __shfl_sync(FULL, code_t, segbase + L);
-                if (inM) {
-                    if (sl < L) stbuf[cnt + sl] = 3;
-                    const int bl = __popc(mm & ((1u << L) - 1u));
-                    cnt += L; ri -= L; rj -= L;
-                    v -= bl * ma + (L - bl) * mi;
-                    i -= L; j -= L;
-                    state = (i >= i0 && j >= j0 && v > 0) ? (codeL >> 2) : 0;
-                } else if (act) {
-                    const int code = dw.load(i, j);
-                    const bool open = (state == 2) ? (code & 2) : (code & 1);
-                    if (sl == 0) stbuf[cnt] = (uint8_t)state;
-                    cnt++;
-                    v -= open ? go : ge;
-                    if (state == 2) { i--; ri--; } else { j--; rj--; }
-                    state = open ? 3 : state;
-                    if (i <= 0 || j <= 0) state = 0;
-                }
-                act = (state != 0 && ri > 0 && rj > 0);
-            }
-            __syncwarp();
-            if (valid) {
-                uint32_t *out = states + (size_t)t * pitch_words;
-                for (int w = sl; w * 16 < cnt; w += LANES) {
-                    uint32_t a = 0;
-#pragma unroll
-                    for (int x = 0; x < 16; x++) {
-                        const int idx = w * 16 + x;
-                        const uint32_t st = (idx < cnt) ? stbuf[idx] : 0u;
-                        a |= st << (2 * x);
-                    }
-                    out[w] = a;
-                }
-                if (sl == 0) {
-                    gact_tile_result r;
-                    r.score = corner;
-                    r.max_i = d.first ? n : d.ref_len;
-                    r.max_j = d.first ? m : d.query_len;
-                    r.n_states = cnt;
-                    r.i_steps = et - ri;
-                    r.j_steps = et - rj;
-                    results[t] = r;
-                }
+            if (sl == 0) {
+                gact_tile_result r;
+                r.score = corner;
+                r.max_i = d.first ? n : d.ref_len;
+                r.max_j = d.first ? m : d.query_len;
+                r.n_states = tr.cnt;
+                r.i_steps = tr.is;
+                r.j_steps = tr.js;
+                results[t] = r;
             }
         }
         __syncwarp();
     }
 }
 
-// ---------------------------------------------------------------------------
-// First-tile pass in the packed domain: score only, plus the position of the LAST maximum in
-// (i outer, j inner) order (align.cpp:173-177).  Per column and half-word the running maximum
-// and the row where it was last reached are kept (VIMNMX.S16x2 with predicate outputs = the
-// reference's `>=` update); columns are then compared by (H, i, j).
+// first-tile kernel: (max_i, max_j) of every first tile
 template <int CS, int LANES, bool LUT>
 __global__ void __launch_bounds__(128, 4)
 gact_first_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *__restrict__ descs,
@@ -338,25 +481,9 @@ gact_first_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *
 {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int TPW = 32 / LANES;
-    constexpr int TS = CS * 2 * LANES;
-    int lane;
-    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
-    const int warp = threadIdx.x >> 5;
-    const int seg = lane / LANES, sl = lane % LANES;
-
-    uint8_t *my = smem + ((size_t)warp * TPW + seg) * seq_bytes;
-    uint32_t *rr = reinterpret_cast<uint32_t *>(my);
-    uint16_t *qs = reinterpret_cast<uint16_t *>(my + (TS + 2) * 4);
-    uint16_t *rb = reinterpret_cast<uint16_t *>(my + (TS + 2) * 6);
-
-    const int B = P.s16_bias;
-    const uint32_t Bp = pk16(B);
-    const uint32_t ma16 = pk16(P.match * 16), mi16 = pk16(P.mismatch * 16);
-    const uint32_t ge16 = pk16(P.gap_extend * 16);
-    const int KO = (P.gap_open * 16) * 65537;
-    const int ONE = P.one;
-    const uint32_t borderD_raw = ((uint32_t)(B + P.gap_open * 16) << 16) | (uint32_t)B;
-    const uint32_t lut_mis = (uint32_t)((P.mismatch * 16) & 0xff) * 0x01010101u;
+    SegCtx<CS, LANES> cx;
+    cx.init(P, smem, threadIdx.x >> 5, seq_bytes, nullptr, 0, 0);
+    const int lane = cx.lane, seg = cx.seg, sl = cx.sl;
 
     for (;;) {
         int t0 = 0;
@@ -369,117 +496,13 @@ gact_first_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *
         d.ref_off = 0; d.query_off = 0; d.ref_len = 0; d.query_len = 0; d.ref_set = 0; d.query_set = 0; d.reverse = 0; d.first = 0;
         if (valid) d = descs[t];
         const int n = d.ref_len, m = d.query_len;
-        const SeqSetDev &rset = P.sets[d.ref_set];
-        const SeqSetDev &qset = P.sets[d.query_set];
-        const bool work = (n > 0 && m > 0);
-
-        __syncwarp();
-        if (work) {
-            for (int x = sl; x <= n + 1; x += LANES) {
-                const bool in = (x >= 1 && x <= n);
-                const int base = in ? tile_base(rset, d.ref_off, d.ref_len, d.reverse, x) : 0;
-                rb[x] = (uint16_t)(in ? enc_base(base) : SENT_R);
-                if (LUT) {
-                    const int code = (base == 'A') ? 0 : (base == 'C') ? 1 : (base == 'G') ? 2 : (base == 'T') ? 3 : 4;
-                    uint32_t w = lut_mis;
-                    if (in && code < 4) w ^= (uint32_t)(((P.match ^ P.mismatch) * 16) & 0xff) << (8 * code);
-                    rr[x] = w;
-                }
-            }
-            for (int x = sl; x <= m; x += LANES)
-                qs[x] = (x >= 1) ? (uint16_t)enc_base(tile_base(qset, d.query_off, d.query_len, d.reverse, x)) : (uint16_t)SENT_Q;
-        }
-        __syncwarp();
-        if (!LUT && work) {
-            for (int x = sl; x <= n + 1; x += LANES)
-                rr[x] = (uint32_t)rb[x] | ((uint32_t)(x >= 1 ? rb[x - 1] : (uint16_t)SENT_R) << 16);
-        }
-        __syncwarp();
-
+        seg_stage<CS, LANES, LUT>(cx, P.sets[d.ref_set], P.sets[d.query_set], d.ref_off, d.ref_len, d.query_off,
+                                  d.query_len, d.reverse, n, m);
         uint32_t q[CS];
-#pragma unroll
-        for (int c = 0; c < CS; c++) {
-            const int jl = (2 * sl) * CS + c + 1, jh = (2 * sl + 1) * CS + c + 1;
-            const uint32_t el = jl <= m ? (uint32_t)qs[jl] : SENT_Q + c, eh = jh <= m ? (uint32_t)qs[jh] : SENT_Q + c;
-            if (LUT) {
-                const uint32_t tl = (el >> 1) & 3u, th = (eh >> 1) & 3u;
-                const uint32_t l2 = (jl <= m) ? (tl ^ (tl >> 1)) : 0u, h2 = (jh <= m) ? (th ^ (th >> 1)) : 0u;
-                q[c] = l2 | ((8u | l2) << 4) | ((4u | h2) << 8) | ((12u | h2) << 12);
-            } else {
-                q[c] = el | (eh << 16);
-            }
-        }
-        const int laststrip = (m > 0) ? (m - 1) / CS : -1;
-        const int lastlane = laststrip >> 1;
-        int steps = work ? n + 1 + 2 * lastlane : 0;
-#pragma unroll
-        for (int o = LANES; o < 32; o <<= 1) steps = max(steps, __shfl_xor_sync(FULL, steps, o));
-        const int kfirst = (work && sl <= lastlane) ? 2 * sl + 1 : 0x3fffffff;
-        const uint32_t *rrp = rr - 2 * sl;
-
-        uint32_t Gup[CS], IoUp[CS], IcUp[CS], best[CS], brow[CS];
-#pragma unroll
-        for (int c = 0; c < CS; c++) {
-            Gup[c] = Bp;
-            IoUp[c] = pk16(B + P.gap_open * 16, S16_NEG);
-            IcUp[c] = pk16(S16_NEG, S16_NEG);
-            best[c] = 0;                               // below every H (H >= B > 0): the first valid cell always updates
-            brow[c] = 0;
-        }
-        uint32_t eG = Bp, eD = pk16(S16_NEG), diag = Bp;
-        for (int k = 1; k <= steps; k++) {
-            const uint32_t pack = __byte_perm(eG, eD, 0x7632);
-            uint32_t recv = __shfl_up_sync(FULL, pack, 1, LANES);
-            if (sl == 0) recv = borderD_raw;
-            const uint32_t inG = __byte_perm(recv, eG, 0x5410);
-            const uint32_t inD = __byte_perm(recv, eD, 0x5432);
-            const int ilo = k - 2 * sl;
-            if ((unsigned)(k - kfirst) <= (unsigned)n) {
-                const uint32_t rlo = rrp[k], rhi = LUT ? rrp[k - 1] : 0u;
-                // rows that do not exist (low half: row n+1, high half: row 0) must not be recorded
-                const uint32_t keep = ((ilo <= n) ? 0x0000ffffu : 0u) | ((ilo >= 2) ? 0xffff0000u : 0u);
-                const uint32_t ipair = pk16(ilo, ilo - 1);
-                uint32_t hd = diag, dv = inD;
-#pragma unroll
-                for (int c = 0; c < CS; c++) {
-                    const uint32_t sc = subst_score<LUT>(q[c], rlo, rhi, ma16, mi16);
-                    const uint32_t mc = __viaddmax_s16x2(hd, sc, Bp);
-                    hd = Gup[c];
-                    const uint32_t iv = __viaddmax_s16x2(IcUp[c], ge16, IoUp[c]);
-                    const uint32_t h = __vimax3_s16x2(mc, iv, dv);
-                    Gup[c] = h;
-                    const uint32_t mo = (uint32_t)((int)mc * ONE + KO);
-                    IoUp[c] = mo;
-                    IcUp[c] = iv;
-                    dv = __viaddmax_s16x2(dv, ge16, mo);
-                    bool ph, pl;
-                    best[c] = __vibmax_s16x2(h & keep, best[c], &ph, &pl);      // pred = (h >= best): last maximum wins
-                    if (pl) brow[c] = __byte_perm(brow[c], ipair, 0x3254);
-                    if (ph) brow[c] = __byte_perm(brow[c], ipair, 0x7610);
-                }
-                eG = Gup[CS - 1];
-                eD = dv;
-                diag = inG;
-            }
-        }
-        // best cell of this lane by (H, i, j); j <= 320 and i <= 320 take 9 bits each here
-        int key = -1;
-#pragma unroll
-        for (int c = 0; c < CS; c++) {
-            const int jl = (2 * sl) * CS + c + 1, jh = (2 * sl + 1) * CS + c + 1;
-            const int hl = (int)(best[c] & 0xffffu), hh = (int)(best[c] >> 16);
-            const int il = (int)(brow[c] & 0xffffu), ih = (int)(brow[c] >> 16);
-            if (work && jl <= m && il >= 1) key = max(key, (((hl - B) >> 4) << 18) | (il << 9) | jl);
-            if (work && jh <= m && ih >= 1) key = max(key, (((hh - B) >> 4) << 18) | (ih << 9) | jh);
-        }
-#pragma unroll
-        for (int o = 1; o < LANES; o <<= 1) key = max(key, __shfl_xor_sync(FULL, key, o));
-        if (valid && sl == 0) {
-            EffLen e;
-            if (key < 0) { e.n = 0; e.m = 0; }
-            else { e.m = key & 511; e.n = (key >> 9) & 511; }
-            eff[t] = e;
-        }
+        seg_load_q<CS, LANES, LUT>(cx, m, q);
+        int mi = 0, mj = 0;
+        seg_first_pass<CS, LANES, LUT>(cx, q, n, m, &mi, &mj);
+        if (valid && sl == 0) { EffLen e; e.n = mi; e.m = mj; eff[t] = e; }
         __syncwarp();
     }
 }
