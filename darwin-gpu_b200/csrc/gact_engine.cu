@@ -73,6 +73,10 @@ struct gact_engine {
     int head = 0, tail = 0, inflight = 0;   // async ring
     bool staged = false;
     double last_kernel_ms = -1.0;
+    ChainCall *d_chain_calls = nullptr;      // gact_engine_extend buffers (grown on demand)
+    ChainResult *d_chain_res = nullptr;
+    size_t chain_cap = 0;
+    cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;
     gact_stats stats{};
     std::string err;
 };
@@ -493,6 +497,10 @@ void gact_engine_destroy(gact_engine *e)
     if (e->d_gscratch) cudaFree(e->d_gscratch);
     s16_free_plan(&e->s16);
     s16h_free_plan(&e->s16h);
+    if (e->d_chain_calls) cudaFree(e->d_chain_calls);
+    if (e->d_chain_res) cudaFree(e->d_chain_res);
+    if (e->ev_c0) cudaEventDestroy(e->ev_c0);
+    if (e->ev_c1) cudaEventDestroy(e->ev_c1);
     if (e->s_h2d) { cudaStreamSynchronize(e->s_h2d); cudaStreamDestroy(e->s_h2d); }
     if (e->s_d2h) { cudaStreamSynchronize(e->s_d2h); cudaStreamDestroy(e->s_d2h); }
     if (e->owns_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -906,5 +914,88 @@ int gact_dsoft_run(gact_dsoft *d, int n_queries, const int32_t *sets, const int6
 }
 
 double gact_dsoft_last_kernel_ms(const gact_dsoft *d) { return d ? d->last_ms : -1.0; }
+
+}  // extern "C"
+
+// ===========================================================================
+// whole candidate extensions on the device
+extern "C" {
+
+int gact_engine_extend_supported(const gact_engine *e)
+{
+    if (!e || !e->s16h.ok || !e->s16h.lut_ok || e->variant_req == 1) return 0;
+    for (int i = 0; i < GACT_MAX_SETS; i++) if (e->sets[i].bits == 8) return 0;
+    return 1;
+}
+
+int gact_engine_extend(gact_engine *e, int n, const gact_call *calls, gact_alignment *out)
+{
+    if (!e || n < 0 || (n > 0 && (!calls || !out))) return GACT_ERR_ARG;
+    if (!gact_engine_extend_supported(e))
+        return fail(e, GACT_ERR_ARG, "on-device extension needs tile_size <= 320, 16-bit score range and ACGT-only sets");
+    if (e->inflight || e->staged) return fail(e, GACT_ERR_STATE, "extend while batches are outstanding");
+    if (n == 0) return GACT_OK;
+    CU(e, cudaSetDevice(e->device));
+    std::vector<ChainCall> cc((size_t)n);
+    const SeqSetHost &rs = e->sets[GACT_SET_REF];
+    for (int i = 0; i < n; i++) {
+        const gact_call &c = calls[i];
+        if (c.query_set >= GACT_MAX_SETS || c.ref_seq < 0 || (size_t)c.ref_seq + 1 >= rs.starts.size())
+            return fail(e, GACT_ERR_ARG, "call " + std::to_string(i) + " out of range");
+        const SeqSetHost &qs = e->sets[c.query_set];
+        if (c.query_seq < 0 || (size_t)c.query_seq + 1 >= qs.starts.size())
+            return fail(e, GACT_ERR_ARG, "call " + std::to_string(i) + " out of range");
+        ChainCall &d = cc[(size_t)i];
+        d.ref_start = rs.starts[(size_t)c.ref_seq];
+        d.query_start = qs.starts[(size_t)c.query_seq];
+        d.ref_len = (int)(rs.starts[(size_t)c.ref_seq + 1] - d.ref_start);
+        d.query_len = (int)(qs.starts[(size_t)c.query_seq + 1] - d.query_start);
+        d.ref_pos = c.ref_pos; d.query_pos = c.query_pos;
+        d.query_set = c.query_set; d.pad = 0;
+        if (c.ref_pos < 0 || c.query_pos < 0 || c.ref_pos > d.ref_len || c.query_pos > d.query_len)
+            return fail(e, GACT_ERR_ARG, "call " + std::to_string(i) + ": anchor outside its sequences");
+    }
+    if ((size_t)n > e->chain_cap) {
+        if (e->d_chain_calls) cudaFree(e->d_chain_calls);
+        if (e->d_chain_res) cudaFree(e->d_chain_res);
+        e->d_chain_calls = nullptr; e->d_chain_res = nullptr; e->chain_cap = 0;
+        if (cudaMalloc(&e->d_chain_calls, (size_t)n * sizeof(ChainCall)) != cudaSuccess ||
+            cudaMalloc(&e->d_chain_res, (size_t)n * sizeof(ChainResult)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(e, GACT_ERR_NOMEM, "cudaMalloc(chain buffers) failed");
+        }
+        e->chain_cap = (size_t)n;
+    }
+    if (!e->ev_c0) { CU(e, cudaEventCreate(&e->ev_c0)); CU(e, cudaEventCreate(&e->ev_c1)); }
+    cudaStream_t st = e->stream;
+    Slot &s = e->slots[0];
+    CU(e, cudaMemcpyAsync(e->d_chain_calls, cc.data(), (size_t)n * sizeof(ChainCall), cudaMemcpyHostToDevice, st));
+    CU(e, cudaMemsetAsync(s.d_counters, 0, 2 * sizeof(int), st));
+    CU(e, cudaEventRecord(e->ev_c0, st));
+    s16h_launch_chain(e->s16h, e->kp, e->d_chain_calls, n, e->d_chain_res, e->params.first_tile_score_threshold,
+                      s.d_counters + 1, st);
+    CU(e, cudaGetLastError());
+    CU(e, cudaEventRecord(e->ev_c1, st));
+    std::vector<ChainResult> res((size_t)n);
+    CU(e, cudaMemcpyAsync(res.data(), e->d_chain_res, (size_t)n * sizeof(ChainResult), cudaMemcpyDeviceToHost, st));
+    CU(e, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e->ev_c0, e->ev_c1);
+    e->last_kernel_ms = ms;
+    e->stats.kernel_ms += ms;
+    e->stats.kernel_launches++;
+    e->stats.batches++;
+    e->stats.h2d_bytes += (double)n * sizeof(ChainCall);
+    e->stats.d2h_bytes += (double)n * sizeof(ChainResult);
+    for (int i = 0; i < n; i++) {
+        const ChainResult &r = res[(size_t)i];
+        gact_alignment &o = out[i];
+        o.ab = r.ab; o.ae = r.ae; o.bb = r.bb; o.be = r.be; o.score = r.score; o.first_tile_score = r.first_tile_score;
+        o.n_tiles = r.n_tiles; o.reserved = 0; o.n_cells = r.n_cells;
+        e->stats.tiles += (uint64_t)r.n_tiles;
+        e->stats.cells += (uint64_t)r.n_cells;
+    }
+    return GACT_OK;
+}
 
 }  // extern "C"

@@ -508,6 +508,152 @@ gact_first_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *
 }
 
 // ---------------------------------------------------------------------------
+// chain kernel ("next" row 2): the whole GACT() of gact.cpp:48-228 per candidate on
+// the device -- left extension, right extension from the first tile's maximum, first-tile threshold,
+// total score -- so a candidate costs no host round trip per tile.  A segment walks one candidate's
+// tile chain; when it finishes it takes the next candidate from the queue.  The per-column score of
+// gact.cpp:197-210 is accumulated inside the traceback (an M run contributes its matches/mismatches,
+// a gap column gap_open or gap_extend depending on the previous column), so no state string is kept.
+// Only for ACGT-only (2-bit packed) sets: there a '-' column test (gact.cpp:201) can never fire.
+struct ChainCall {
+    long long ref_start, query_start;     // offsets of the two sequences in their sets
+    int ref_len, query_len;               // full sequence lengths
+    int ref_pos, query_pos;               // D-SOFT anchor (darwin.cpp:216-224)
+    int query_set, pad;
+};
+struct ChainResult {
+    int ab, ae, bb, be, score, first_tile_score, n_tiles, pad;
+    long long n_cells;
+};
+
+template <int CS, int LANES>
+__global__ void __launch_bounds__(128, 3)
+gact_chain_s16h_kernel(const __grid_constant__ KParams P, const ChainCall *__restrict__ calls, int n_calls,
+                       ChainResult *__restrict__ results, int thr, int *counter, size_t seq_bytes,
+                       uint8_t *gscratch, size_t dir_bytes)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr unsigned SEGBITS = (LANES == 32) ? 0xffffffffu : ((1u << LANES) - 1u);
+    SegCtx<CS, LANES> cx;
+    cx.init(P, smem, threadIdx.x >> 5, seq_bytes, gscratch, dir_bytes, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+    const int sl = cx.sl;
+    const unsigned segmask = SEGBITS << cx.segbase;
+    const int T = P.tile_size;
+    const SeqSetDev &rset = P.sets[GACT_SET_REF];
+
+    // candidate state, replicated in every lane of the segment (the locals of GACT(), gact.cpp:51-80)
+    int call = -1;
+    ChainCall c;
+    c.ref_start = 0; c.query_start = 0; c.ref_len = 0; c.query_len = 0; c.ref_pos = 0; c.query_pos = 0; c.query_set = 0; c.pad = 0;
+    int rp = 0, qp = 0, rrp = 0, rqp = 0, ab = 0, bb = 0, score = 0, fts = 0, n_tiles = 0;
+    long long n_cells = 0;
+    int phase = 2, first_tile = 0, prev_gap = 0, anchor_gap = 0, left_any = 0, adv = 1;
+    bool alive = true;                       // false once the queue is empty for this segment
+
+    for (;;) {
+        // ---- next tile of this segment's candidate (loop heads of gact.cpp:82 and :144) ----
+        int t_rl = 0, t_ql = 0, reverse = 0;
+        long long roff = 0, qoff = 0;
+        bool have = false;
+        while (alive && !have) {
+            if (phase == 2) {
+                if (call >= 0 && sl == 0) {
+                    ChainResult r;
+                    r.ab = ab; r.bb = bb; r.ae = rp; r.be = qp; r.score = score; r.first_tile_score = fts;
+                    r.n_tiles = n_tiles; r.pad = 0; r.n_cells = n_cells;
+                    results[call] = r;
+                }
+                int nxt = 0;
+                if (sl == 0) nxt = atomicAdd(counter, 1);
+                nxt = __shfl_sync(segmask, nxt, cx.segbase);
+                if (nxt >= n_calls) { alive = false; call = -1; break; }
+                call = nxt;
+                c = calls[call];
+                rp = rrp = c.ref_pos; qp = rqp = c.query_pos;
+                ab = bb = 0; score = 0; fts = 0; n_tiles = 0; n_cells = 0;
+                phase = 0; first_tile = 1; prev_gap = 0; anchor_gap = 0; left_any = 0; adv = 1;
+            }
+            if (phase == 0) {
+                if (rp > 0 && qp > 0 && (adv || first_tile)) {
+                    t_rl = rp > T ? T : rp;
+                    t_ql = qp > T ? T : qp;
+                    roff = c.ref_start + rp - t_rl;
+                    qoff = c.query_start + qp - t_ql;
+                    reverse = 0;
+                    have = true;
+                } else {
+                    ab = rp; bb = qp; rp = rrp; qp = rqp;          // gact.cpp:136-141
+                    phase = 1;
+                    prev_gap = left_any ? anchor_gap : 0;
+                    adv = 1;
+                }
+            }
+            if (phase == 1 && !have) {
+                if (rp < c.ref_len && qp < c.query_len && (adv || first_tile)) {
+                    t_rl = (rp + T < c.ref_len) ? T : c.ref_len - rp;
+                    t_ql = (qp + T < c.query_len) ? T : c.query_len - qp;
+                    roff = c.ref_start + rp;
+                    qoff = c.query_start + qp;
+                    reverse = 1;
+                    have = true;
+                } else {
+                    phase = 2;
+                }
+            }
+        }
+        if (!__any_sync(FULL, have)) break;
+
+        // ---- the tile: stage, (first pass), DP, traceback ----
+        int n = have ? t_rl : 0, m = have ? t_ql : 0;
+        const SeqSetDev &qset = P.sets[c.query_set];
+        seg_stage<CS, LANES, true>(cx, rset, qset, roff, t_rl, qoff, t_ql, reverse, n, m);
+        uint32_t q[CS];
+        seg_load_q<CS, LANES, true>(cx, m, q);
+        const bool is_first = have && first_tile;
+        int mi = n, mj = m;
+        if (__any_sync(FULL, is_first)) {
+            int fi = 0, fj = 0;
+            seg_first_pass<CS, LANES, true>(cx, q, is_first ? n : 0, is_first ? m : 0, &fi, &fj);
+            if (is_first) { mi = fi; mj = fj; n = fi; m = fj; }           // sub-tile ending at the last maximum
+        }
+        DirWinH<CS> dw;
+        dw.init(cx.dirbase, n, m, P);
+        const int tile_score = seg_dp<CS, LANES, true>(cx, q, n, m, dw);
+        const SegTrace tr = seg_traceback<CS, LANES, false>(cx, dw, n, m, tile_score, nullptr, prev_gap);
+
+        // ---- consume (bodies of the loops at gact.cpp:95-133 and :158-194) ----
+        if (have) {
+            const bool left = (phase == 0);
+            n_tiles++;
+            n_cells += (long long)t_rl * t_ql;
+            bool skip = false;
+            if (first_tile) {
+                if (left) { rp = rp - t_rl + mi; qp = qp - t_ql + mj; rrp = rp; rqp = qp; }
+                else      { rp = rp + t_rl - mi; qp = qp + t_ql - mj; }
+                fts = tile_score;
+                if (tile_score < thr) {                                    // gact.cpp:107-109 / :168-170
+                    if (left) { ab = rp; bb = qp; rp = rrp; qp = rqp; phase = 1; prev_gap = 0; adv = 1; }
+                    else      { phase = 2; }
+                    skip = true;
+                }
+            }
+            if (!skip) {
+                if (tr.cnt > 0) {
+                    first_tile = 0;
+                    score += tr.col_score;
+                    prev_gap = tr.last_gap;
+                    if (left && !left_any) { left_any = 1; anchor_gap = tr.first_gap; }
+                }
+                if (left) { rp -= tr.is; qp -= tr.js; } else { rp += tr.is; qp += tr.js; }
+                if (first_tile && tr.cnt == 0) { first_tile = 0; adv = 0; }
+                else adv = (tr.is > 0 && tr.js > 0) ? 1 : 0;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 struct S16HPlan {
     bool ok = false;
@@ -579,8 +725,25 @@ inline int s16h_make_plan(const gact_params &p, int num_sms, int warps_per_sm, S
             cudaFuncSetAttribute((const void *)s16h_pick_first(CS, lut != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)pl->smem) != cudaSuccess)
             return -1;
+    if (cudaFuncSetAttribute((const void *)(CS == 8 ? (const void *)gact_chain_s16h_kernel<8, 16> : (const void *)gact_chain_s16h_kernel<10, 16>),
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem) != cudaSuccess)
+        return -1;
     pl->ok = true;
     return 0;
+}
+
+inline void s16h_launch_chain(const S16HPlan &pl, KParams kp, const ChainCall *calls, int n_calls, ChainResult *results,
+                              int thr, int *counter, cudaStream_t st)
+{
+    kp.win_rows = pl.win_rows;
+    kp.win_lanes = pl.win_lanes;
+    kp.s16_bias = pl.bias;
+    kp.one = 1;
+    int ctas = pl.ctas;
+    const int need = (n_calls + pl.warps_per_cta * 2 - 1) / (pl.warps_per_cta * 2);
+    if (need < ctas) ctas = need;
+    if (pl.CS == 8) gact_chain_s16h_kernel<8, 16><<<ctas, pl.warps_per_cta * 32, pl.smem, st>>>(kp, calls, n_calls, results, thr, counter, pl.seq_bytes, pl.d_scratch, pl.dir_bytes);
+    else gact_chain_s16h_kernel<10, 16><<<ctas, pl.warps_per_cta * 32, pl.smem, st>>>(kp, calls, n_calls, results, thr, counter, pl.seq_bytes, pl.d_scratch, pl.dir_bytes);
 }
 
 inline void s16h_launch_first(const S16HPlan &pl, KParams kp, const gact_tile_desc *descs, const int *first_list,

@@ -10,6 +10,8 @@
 //   DARWIN_GPUS=<n>      GPUs to use (default: all visible); reads are sharded contiguously
 //                        by ceil(num_reads / n), one host scheduler thread + engine per GPU
 //   DARWIN_KERNEL=<0|1|2> kernel variant (auto / int32 / s16x2)
+//   DARWIN_CHAINS=<1|0>   1 (default): whole candidate extensions on the device (gact_engine_extend) when the
+//                        engine supports it; 0: tile-by-tile host scheduler (GactScheduler)
 //   DARWIN_DSOFT=<gpu|host> where the D-SOFT filter runs (default gpu: gact_dsoft_run on the shard's GPU;
 //                        host: SeedTable::dsoft on CPU_THREADS / n host threads)
 //
@@ -86,6 +88,7 @@ int main(int argc, char **argv)
     int want_gpus = ndev;
     if (const char *e = getenv("DARWIN_GPUS")) want_gpus = std::max(1, std::min(ndev, atoi(e)));
     const int kernel_variant = getenv("DARWIN_KERNEL") ? atoi(getenv("DARWIN_KERNEL")) : 0;
+    const bool use_chains = !(getenv("DARWIN_CHAINS") && atoi(getenv("DARWIN_CHAINS")) == 0);
     const bool dsoft_on_gpu = !(getenv("DARWIN_DSOFT") && std::string(getenv("DARWIN_DSOFT")) == "host");
     printf("Using GPU: %d device(s), CPU threads: %d\n", want_gpus, num_threads);
     printf("Scores: match = %d, mismatch = %d, gap_open = %d, gap_extend = %d\n", cfg.match, cfg.mismatch, cfg.gap_open, cfg.gap_extend);
@@ -295,8 +298,39 @@ int main(int argc, char **argv)
             // query ids inside the engine are shard-local
             for (auto &c : calls) c.query_id -= (int32_t)sh.first_read;
             std::vector<GactAlignment> aln;
-            GactScheduler sched(eng, gp, ref_views, rd, rc_views, sh.dsoft_threads);
-            sched.run(calls, aln, &sh.stats);
+            if (use_chains && gact_engine_extend_supported(eng)) {
+                // whole GACT() per candidate on the device; longest reads first (their chains are the longest)
+                std::vector<uint32_t> ord(calls.size());
+                for (size_t k = 0; k < ord.size(); k++) ord[k] = (uint32_t)k;
+                std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) {
+                    return rd[(size_t)calls[a].query_id].len > rd[(size_t)calls[b].query_id].len;
+                });
+                std::vector<gact_call> gc(calls.size());
+                for (size_t k = 0; k < ord.size(); k++) {
+                    const GactCall &c = calls[ord[k]];
+                    gact_call g;
+                    memset(&g, 0, sizeof(g));
+                    g.ref_seq = c.ref_id; g.query_seq = c.query_id; g.ref_pos = c.ref_pos; g.query_pos = c.query_pos;
+                    g.query_set = c.complement ? GACT_SET_READS_RC : GACT_SET_READS;
+                    gc[k] = g;
+                }
+                std::vector<gact_alignment> ga(calls.size());
+                auto tc = Clock::now();
+                int rc2 = gact_engine_extend(eng, (int)gc.size(), gc.data(), ga.data());
+                if (rc2) { sh.error = std::string("gact_engine_extend: ") + gact_last_error(eng); return; }
+                sh.stats.wall_ms += std::chrono::duration<double, std::milli>(Clock::now() - tc).count();
+                aln.resize(calls.size());
+                for (size_t k = 0; k < ord.size(); k++) {
+                    const gact_alignment &a = ga[k];
+                    aln[ord[k]] = GactAlignment{a.ab, a.ae, a.bb, a.be, a.score, a.first_tile_score, a.n_tiles, a.n_cells};
+                    sh.stats.tiles += (uint64_t)a.n_tiles;
+                    sh.stats.cells += (uint64_t)a.n_cells;
+                }
+                sh.stats.rounds += 1;
+            } else {
+                GactScheduler sched(eng, gp, ref_views, rd, rc_views, sh.dsoft_threads);
+                sched.run(calls, aln, &sh.stats);
+            }
             gact_stats es;
             gact_engine_stats(eng, &es);
             sh.stats.device_ms = es.kernel_ms;

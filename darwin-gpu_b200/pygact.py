@@ -53,9 +53,14 @@ EXPORTS = [
     "gact_engine_stage", "gact_engine_run_staged", "gact_engine_fetch_staged", "gact_engine_sync",
     "gact_engine_last_kernel_ms", "gact_engine_stats", "gact_engine_reset_stats",
     "gact_engine_set_kernel", "gact_engine_get_kernel", "gact_int_peak",
+    "gact_engine_extend", "gact_engine_extend_supported",
     "gact_dsoft_create", "gact_dsoft_destroy", "gact_dsoft_run", "gact_dsoft_last_kernel_ms",
 ]
 
+CALL_DTYPE = np.dtype([("ref_seq", "<i4"), ("query_seq", "<i4"), ("ref_pos", "<i4"), ("query_pos", "<i4"),
+                       ("query_set", "u1"), ("reserved", "u1", (3,))])
+ALIGNMENT_DTYPE = np.dtype([("ab", "<i4"), ("ae", "<i4"), ("bb", "<i4"), ("be", "<i4"), ("score", "<i4"),
+                            ("first_tile_score", "<i4"), ("n_tiles", "<i4"), ("reserved", "<i4"), ("n_cells", "<i8")])
 DSOFT_CAND_DTYPE = np.dtype([("query", "<i4"), ("seq", "<i4"), ("hit", "<u4"), ("offset", "<u4")])
 
 _lib = None
@@ -119,6 +124,10 @@ def load():
     L.gact_engine_set_kernel.argtypes = [vp, i32]
     L.gact_engine_get_kernel.restype = i32
     L.gact_engine_get_kernel.argtypes = [vp]
+    L.gact_engine_extend.restype = i32
+    L.gact_engine_extend.argtypes = [vp, i32, vp, vp]
+    L.gact_engine_extend_supported.restype = i32
+    L.gact_engine_extend_supported.argtypes = [vp]
     L.gact_dsoft_create.restype = i32
     L.gact_dsoft_create.argtypes = [C.POINTER(vp), vp, vp, C.c_uint64, vp, C.c_uint64, i32, i32, C.c_uint32,
                                     C.c_uint32, i32, i32, i32]
@@ -261,6 +270,16 @@ class GactEngine:
                                                  st.ctypes.data if want_states else None),
                  "gact_engine_fetch_staged")
         return res, st
+
+    def extend_supported(self):
+        return bool(self.L.gact_engine_extend_supported(self.h))
+
+    def extend(self, calls):
+        """Whole GACT() extensions on the device; calls: CALL_DTYPE array -> ALIGNMENT_DTYPE array."""
+        calls = np.ascontiguousarray(calls, dtype=CALL_DTYPE)
+        out = np.zeros(len(calls), dtype=ALIGNMENT_DTYPE)
+        self._ck(self.L.gact_engine_extend(self.h, len(calls), calls.ctypes.data, out.ctypes.data), "gact_engine_extend")
+        return out
 
     def stats(self):
         s = Stats()

@@ -198,6 +198,34 @@ int gact_engine_reset_stats(gact_engine *e);
 int gact_engine_set_kernel(gact_engine *e, int variant);
 int gact_engine_get_kernel(const gact_engine *e);
 
+/* ---- whole candidate extensions on the device (GACT(), gact.cpp:48-228) ----
+ * One call = one D-SOFT candidate: left extension, right extension from the first tile's maximum,
+ * first-tile threshold, total score -- the tile chain is walked on the GPU, the host gets one
+ * gact_alignment per call and no traceback states.  Supported when the packed two-tiles-per-warp kernel
+ * can run the engine's parameters (tile_size <= 320, scores in the 16-bit range) and the sets in use
+ * hold only ACGT; otherwise GACT_ERR_ARG is returned and the caller drives tiles itself
+ * (gact_engine_submit/wait, as host/gact_scheduler.cpp does). */
+typedef struct {
+    int32_t ref_seq;      /* sequence index inside GACT_SET_REF                    */
+    int32_t query_seq;    /* sequence index inside query_set                       */
+    int32_t ref_pos;      /* anchor (darwin.cpp:216-224)                           */
+    int32_t query_pos;
+    uint8_t query_set;    /* GACT_SET_READS or GACT_SET_READS_RC                   */
+    uint8_t reserved[3];
+} gact_call;
+
+typedef struct {
+    int32_t ab, ae, bb, be;       /* gact.cpp:219-222                               */
+    int32_t score;                /* total score, gact.cpp:197-210                  */
+    int32_t first_tile_score;
+    int32_t n_tiles;
+    int32_t reserved;
+    int64_t n_cells;              /* sum ref_len*query_len over the tiles aligned   */
+} gact_alignment;
+
+int gact_engine_extend(gact_engine *e, int n, const gact_call *calls, gact_alignment *out);
+int gact_engine_extend_supported(const gact_engine *e);      /* 1 / 0 */
+
 /* ---- D-SOFT candidate filter on the device (seed_pos_table.cpp:100-167, ntcoding.cpp:155-182) ----
  * The seed-position table (index_table_: 4^k + 1 entries, pos_table_) is built by the host
  * (SeedPosTable constructor, seed_pos_table.cpp:46-98) and uploaded once; queries are sequences of
