@@ -391,26 +391,26 @@ __device__ __forceinline__ void seg_first_pass(const SegCtx<CS, LANES> &cx, cons
             diag = inG;
         }
     }
-    // best cell of this lane by (H, i, j); i, j <= 320 take 9 bits each here
-    int key = -1;
+    // best cell of this lane by (H, i, j); i, j <= 1024 take 11 bits each
+    long long key = -1;
 #pragma unroll
     for (int c = 0; c < CS; c++) {
         const int jl = (2 * sl) * CS + c + 1, jh = (2 * sl + 1) * CS + c + 1;
         const int hl = (int)(best[c] & 0xffffu), hh = (int)(best[c] >> 16);
         const int il = (int)(brow[c] & 0xffffu), ih = (int)(brow[c] >> 16);
-        if (work && jl <= m && il >= 1) key = max(key, (((hl - B) >> 4) << 18) | (il << 9) | jl);
-        if (work && jh <= m && ih >= 1) key = max(key, (((hh - B) >> 4) << 18) | (ih << 9) | jh);
+        if (work && jl <= m && il >= 1) key = max(key, ((long long)((hl - B) >> 4) << 22) | ((long long)il << 11) | jl);
+        if (work && jh <= m && ih >= 1) key = max(key, ((long long)((hh - B) >> 4) << 22) | ((long long)ih << 11) | jh);
     }
 #pragma unroll
     for (int o = 1; o < LANES; o <<= 1) key = max(key, __shfl_xor_sync(FULL, key, o));
     if (key < 0) { *max_i = 0; *max_j = 0; }
-    else { *max_j = key & 511; *max_i = (key >> 9) & 511; }
+    else { *max_j = (int)(key & 2047); *max_i = (int)((key >> 11) & 2047); }
 }
 
 // ---------------------------------------------------------------------------
 // tile kernel: one tile per segment, results + packed states to global memory
 template <int CS, int LANES, bool LUT>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, (CS <= 10 ? 4 : 2))
 gact_tile_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *__restrict__ descs,
                       const int *__restrict__ order, int n_tiles, const EffLen *__restrict__ eff,
                       gact_tile_result *__restrict__ results, uint32_t *__restrict__ states,
@@ -474,7 +474,7 @@ gact_tile_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *_
 
 // first-tile kernel: (max_i, max_j) of every first tile
 template <int CS, int LANES, bool LUT>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, (CS <= 10 ? 4 : 2))
 gact_first_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *__restrict__ descs,
                        const int *__restrict__ first_list, int n_first, EffLen *__restrict__ eff, int *counter,
                        size_t seq_bytes)
@@ -527,7 +527,7 @@ struct ChainResult {
 };
 
 template <int CS, int LANES>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, (CS <= 10 ? 3 : 2))
 gact_chain_s16h_kernel(const __grid_constant__ KParams P, const ChainCall *__restrict__ calls, int n_calls,
                        ChainResult *__restrict__ results, int thr, int *counter, size_t seq_bytes,
                        uint8_t *gscratch, size_t dir_bytes)
@@ -661,26 +661,53 @@ struct S16HPlan {
     bool lut_ok = false;
     size_t seq_bytes = 0, smem = 0, dir_bytes = 0;
     uint8_t *d_scratch = nullptr;
+    int tpw() const { return 32 / lanes; }
 };
 
 typedef void (*s16h_fn)(const KParams, const gact_tile_desc *, const int *, int, const EffLen *, gact_tile_result *,
                         uint32_t *, int, int *, size_t, uint8_t *, size_t);
-inline s16h_fn s16h_pick(int CS, bool lut)
-{
-    switch (CS) {
-        case 8: return lut ? gact_tile_s16h_kernel<8, 16, true> : gact_tile_s16h_kernel<8, 16, false>;
-        case 10: return lut ? gact_tile_s16h_kernel<10, 16, true> : gact_tile_s16h_kernel<10, 16, false>;
-        default: return nullptr;
-    }
-}
-
 typedef void (*s16h_first_fn)(const KParams, const gact_tile_desc *, const int *, int, EffLen *, int *, size_t);
-inline s16h_first_fn s16h_pick_first(int CS, bool lut)
+typedef void (*s16h_chain_fn)(const KParams, const ChainCall *, int, ChainResult *, int, int *, size_t, uint8_t *, size_t);
+
+// (strip width, lanes per tile): T <= 256: (8,16), <= 320: (10,16), <= 512: (8,32), <= 1024: (16,32)
+#define S16H_DISPATCH(CSV, LANESV, EXPR_CS_LANES)                         \
+    do {                                                                  \
+        if ((CSV) == 8 && (LANESV) == 16) { EXPR_CS_LANES(8, 16); }       \
+        else if ((CSV) == 10 && (LANESV) == 16) { EXPR_CS_LANES(10, 16); } \
+        else if ((CSV) == 8 && (LANESV) == 32) { EXPR_CS_LANES(8, 32); }  \
+        else { EXPR_CS_LANES(16, 32); }                                   \
+    } while (0)
+
+inline s16h_fn s16h_pick(int CS, int lanes, bool lut)
+{
+    s16h_fn f = nullptr;
+#define S16H_X(C, L) f = lut ? gact_tile_s16h_kernel<C, L, true> : gact_tile_s16h_kernel<C, L, false>
+    S16H_DISPATCH(CS, lanes, S16H_X);
+#undef S16H_X
+    return f;
+}
+inline s16h_first_fn s16h_pick_first(int CS, int lanes, bool lut)
+{
+    s16h_first_fn f = nullptr;
+#define S16H_X(C, L) f = lut ? gact_first_s16h_kernel<C, L, true> : gact_first_s16h_kernel<C, L, false>
+    S16H_DISPATCH(CS, lanes, S16H_X);
+#undef S16H_X
+    return f;
+}
+inline s16h_chain_fn s16h_pick_chain(int CS, int lanes)
+{
+    s16h_chain_fn f = nullptr;
+#define S16H_X(C, L) f = gact_chain_s16h_kernel<C, L>
+    S16H_DISPATCH(CS, lanes, S16H_X);
+#undef S16H_X
+    return f;
+}
+inline size_t s16h_dir_bytes(int CS, int rows, int lanes)
 {
     switch (CS) {
-        case 8: return lut ? gact_first_s16h_kernel<8, 16, true> : gact_first_s16h_kernel<8, 16, false>;
-        case 10: return lut ? gact_first_s16h_kernel<10, 16, true> : gact_first_s16h_kernel<10, 16, false>;
-        default: return nullptr;
+        case 8: return DirWinH<8>::bytes(rows, lanes);
+        case 10: return DirWinH<10>::bytes(rows, lanes);
+        default: return DirWinH<16>::bytes(rows, lanes);
     }
 }
 
@@ -690,46 +717,55 @@ inline void s16h_free_plan(S16HPlan *pl)
     pl->d_scratch = nullptr;
 }
 
-// Two tiles per warp for tile_size <= 320 (CS = 8 up to 256, CS = 10 up to 320).
+// Two tiles per warp for tile_size <= 320, one tile per warp up to 1024.
 inline int s16h_make_plan(const gact_params &p, int num_sms, int warps_per_sm, S16HPlan *pl)
 {
     s16h_free_plan(pl);
     *pl = S16HPlan();
     const int T = p.tile_size, et = p.tile_size - p.tile_overlap;
-    if (T > 320) return 0;
     const int bias = 16 * (-p.gap_open + 2);
     pl->bias = bias;
     pl->lut_ok = (p.match * 16 <= 127 && p.mismatch * 16 >= -128);
     const long hi = (long)T * (p.match > 0 ? p.match : 0) * 16 + 16 + bias;
     if (hi > 30000 || p.mismatch > 0 || p.match < 0 || p.gap_open < -500 || p.gap_extend < -500 || p.mismatch < -1000)
         return 0;
-    const int CS = (T <= 256) ? 8 : 10;
-    pl->CS = CS;
+    int CS, lanes;
+    if (T <= 256) { CS = 8; lanes = 16; } else if (T <= 320) { CS = 10; lanes = 16; }
+    else if (T <= 512) { CS = 8; lanes = 32; } else { CS = 16; lanes = 32; }
+    pl->CS = CS; pl->lanes = lanes;
     pl->win_rows = (et + 1 < T) ? et + 1 : T;
     int wl = et / (2 * CS) + 2;
-    pl->win_lanes = wl > 16 ? 16 : wl;
-    const int TS = CS * 32;
+    pl->win_lanes = wl > lanes ? lanes : wl;
+    const int TS = CS * 2 * lanes;
     pl->seq_bytes = (size_t)(((TS + 2) * 8 + 15) & ~15);
-    pl->dir_bytes = (CS == 8) ? DirWinH<8>::bytes(pl->win_rows, pl->win_lanes) : DirWinH<10>::bytes(pl->win_rows, pl->win_lanes);
+    pl->dir_bytes = s16h_dir_bytes(CS, pl->win_rows, pl->win_lanes);
     int wps = warps_per_sm > 0 ? warps_per_sm : 16;
-    if (wps > 16) wps = 16;
+    const int wps_max = (CS <= 10) ? 16 : 8;
+    if (wps > wps_max) wps = wps_max;
     pl->warps_per_cta = 4;
     const int c = (wps + 3) / 4;
     pl->ctas = c * num_sms;
-    pl->smem = (size_t)pl->warps_per_cta * 2 * pl->seq_bytes;
-    const size_t total = (size_t)pl->ctas * pl->warps_per_cta * 2 * pl->dir_bytes;
+    pl->smem = (size_t)pl->warps_per_cta * pl->tpw() * pl->seq_bytes;
+    const size_t total = (size_t)pl->ctas * pl->warps_per_cta * pl->tpw() * pl->dir_bytes;
     if (cudaMalloc(&pl->d_scratch, total) != cudaSuccess) { cudaGetLastError(); pl->d_scratch = nullptr; return 0; }
     for (int lut = 0; lut < 2; lut++)
-        if (cudaFuncSetAttribute((const void *)s16h_pick(CS, lut != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute((const void *)s16h_pick(CS, lanes, lut != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)pl->smem) != cudaSuccess ||
-            cudaFuncSetAttribute((const void *)s16h_pick_first(CS, lut != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaFuncSetAttribute((const void *)s16h_pick_first(CS, lanes, lut != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)pl->smem) != cudaSuccess)
             return -1;
-    if (cudaFuncSetAttribute((const void *)(CS == 8 ? (const void *)gact_chain_s16h_kernel<8, 16> : (const void *)gact_chain_s16h_kernel<10, 16>),
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem) != cudaSuccess)
+    if (cudaFuncSetAttribute((const void *)s16h_pick_chain(CS, lanes), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)pl->smem) != cudaSuccess)
         return -1;
     pl->ok = true;
     return 0;
+}
+
+inline int s16h_grid(const S16HPlan &pl, int n_items)
+{
+    const int per_cta = pl.warps_per_cta * pl.tpw();
+    const int need = (n_items + per_cta - 1) / per_cta;
+    return need < pl.ctas ? need : pl.ctas;
 }
 
 inline void s16h_launch_chain(const S16HPlan &pl, KParams kp, const ChainCall *calls, int n_calls, ChainResult *results,
@@ -739,11 +775,8 @@ inline void s16h_launch_chain(const S16HPlan &pl, KParams kp, const ChainCall *c
     kp.win_lanes = pl.win_lanes;
     kp.s16_bias = pl.bias;
     kp.one = 1;
-    int ctas = pl.ctas;
-    const int need = (n_calls + pl.warps_per_cta * 2 - 1) / (pl.warps_per_cta * 2);
-    if (need < ctas) ctas = need;
-    if (pl.CS == 8) gact_chain_s16h_kernel<8, 16><<<ctas, pl.warps_per_cta * 32, pl.smem, st>>>(kp, calls, n_calls, results, thr, counter, pl.seq_bytes, pl.d_scratch, pl.dir_bytes);
-    else gact_chain_s16h_kernel<10, 16><<<ctas, pl.warps_per_cta * 32, pl.smem, st>>>(kp, calls, n_calls, results, thr, counter, pl.seq_bytes, pl.d_scratch, pl.dir_bytes);
+    s16h_pick_chain(pl.CS, pl.lanes)<<<s16h_grid(pl, n_calls), pl.warps_per_cta * 32, pl.smem, st>>>(
+        kp, calls, n_calls, results, thr, counter, pl.seq_bytes, pl.d_scratch, pl.dir_bytes);
 }
 
 inline void s16h_launch_first(const S16HPlan &pl, KParams kp, const gact_tile_desc *descs, const int *first_list,
@@ -753,11 +786,8 @@ inline void s16h_launch_first(const S16HPlan &pl, KParams kp, const gact_tile_de
     kp.one = 1;
     bool lut = pl.lut_ok;
     for (int i = 0; i < GACT_MAX_SETS; i++) if (kp.sets[i].bytes) lut = false;
-    int ctas = pl.ctas;
-    const int need = (n_first + pl.warps_per_cta * 2 - 1) / (pl.warps_per_cta * 2);
-    if (need < ctas) ctas = need;
-    s16h_pick_first(pl.CS, lut)<<<ctas, pl.warps_per_cta * 32, pl.smem, st>>>(kp, descs, first_list, n_first, eff, counter,
-                                                                             pl.seq_bytes);
+    s16h_pick_first(pl.CS, pl.lanes, lut)<<<s16h_grid(pl, n_first), pl.warps_per_cta * 32, pl.smem, st>>>(
+        kp, descs, first_list, n_first, eff, counter, pl.seq_bytes);
 }
 
 inline void s16h_launch(const S16HPlan &pl, KParams kp, const gact_tile_desc *descs, const int *order, int n,
@@ -770,12 +800,8 @@ inline void s16h_launch(const S16HPlan &pl, KParams kp, const gact_tile_desc *de
     kp.one = 1;
     bool lut = pl.lut_ok;
     for (int i = 0; i < GACT_MAX_SETS; i++) if (kp.sets[i].bytes) lut = false;
-    int ctas = pl.ctas;
-    const int need = (n + pl.warps_per_cta * 2 - 1) / (pl.warps_per_cta * 2);
-    if (need < ctas) ctas = need;
-    s16h_pick(pl.CS, lut)<<<ctas, pl.warps_per_cta * 32, pl.smem, st>>>(kp, descs, order, n, eff, results, states,
-                                                                       pitch_words, counter, pl.seq_bytes,
-                                                                       pl.d_scratch, pl.dir_bytes);
+    s16h_pick(pl.CS, pl.lanes, lut)<<<s16h_grid(pl, n), pl.warps_per_cta * 32, pl.smem, st>>>(
+        kp, descs, order, n, eff, results, states, pitch_words, counter, pl.seq_bytes, pl.d_scratch, pl.dir_bytes);
 }
 
 }  // namespace gact

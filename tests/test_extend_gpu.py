@@ -35,7 +35,8 @@ def make_case(seed, n_reads=40, genome_len=120000, tile=320):
 
 
 @pytest.mark.parametrize("tile,overlap,scores", [(320, 120, (1, -1, -1, -1)), (256, 96, (1, -1, -1, -1)),
-                                                 (320, 120, (2, -3, -5, -2)), (300, 100, (1, -1, -2, -1))])
+                                                 (320, 120, (2, -3, -5, -2)), (300, 100, (1, -1, -2, -1)),
+                                                 (512, 192, (1, -1, -1, -1)), (1024, 384, (1, -1, -1, -1))])
 def test_extend_matches_oracle_gact(pygact, oracle, tile, overlap, scores):
     G, O = pygact, oracle
     genome, reads, rc, calls = make_case(tile + overlap + scores[0])
