@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 int32, 2 s16x2")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reads-leg", action="store_true", help="skip the application-level reads/s leg")
     return ap.parse_args()
 
 
@@ -179,6 +180,41 @@ def reference_main(args):
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def reads_leg(n_gpus):
+    """Application-level leg of the metric: reads/s of the drop-in `darwin` binary (C++ host + engine) in the
+    reference's own timed bracket ("seed table querying + aligning", darwin.cpp:615-639) on a bounded config-3-shaped
+    workload: 25 MB of PacBio-like ~10 kb reads against a 20 Mbp reference, reads sharded over n_gpus GPUs."""
+    import re
+    import tempfile
+    import synth
+    exe = os.path.join(ROOT, "darwin-gpu_b200", "darwin")
+    if not os.path.exists(exe):
+        return {"unavailable": "darwin-gpu_b200/darwin not built"}
+    wd = tempfile.mkdtemp(prefix="bench_reads_")
+    rng = np.random.default_rng(3)
+    genome = [synth.random_genome(1000000, rng) for _ in range(20)]
+    synth.write_fasta(os.path.join(wd, "ref.fasta"), [f"chr{i}" for i in range(20)], genome)
+    names, reads = synth.sample_reads(genome, 25_000_000, np.random.default_rng(4), mean=10000, sd=3000, lo=1000, hi=30000)
+    synth.write_fasta(os.path.join(wd, "reads.fasta"), names, reads)
+    open(os.path.join(wd, "params.cfg"), "w").write(open(os.path.join(ROOT, "darwin-gpu_b200", "params.cfg")).read())
+    r = subprocess.run([exe, "ref.fasta", "reads.fasta", str(os.cpu_count() or 1)], cwd=wd, capture_output=True, text=True,
+                       env=dict(os.environ, DARWIN_GPUS=str(n_gpus)), timeout=600)
+    if r.returncode != 0:
+        return {"unavailable": "darwin exited %d: %s" % (r.returncode, r.stderr[-200:])}
+    summ = json.loads(re.search(r"DARWIN_B200_SUMMARY (\{.*\})", r.stdout).group(1))
+    lines = 0
+    for fn in os.listdir(wd):
+        if fn.startswith("darwin.") and fn.endswith(".out"):
+            lines += sum(1 for _ in open(os.path.join(wd, fn)))
+    align_s = max(summ["align_phase_ms"], 1) / 1e3
+    return {"reads_per_s": len(reads) / align_s, "align_phase_ms": summ["align_phase_ms"], "reads": len(reads),
+            "read_bases": int(sum(len(x) for x in reads)), "gpus": n_gpus, "tiles": summ["tiles"], "cells": summ["cells"],
+            "gcups_align_phase": summ["cells"] / align_s / 1e9, "overlap_lines": lines,
+            "workload": "config3-shaped, bounded: 25 MB PacBio-like ~10 kb reads vs 20 x 1 Mbp reference, params.cfg "
+                        "defaults, D-SOFT + GACT extension on the GPU, timed bracket = the reference's "
+                        "'seed table querying + aligning'"}
 
 
 def shard_range(n_items, world, rank):
@@ -346,10 +382,19 @@ def main():
             small = {k: (v[:1 << 15] if k not in ("ref", "query") else v) for k, v in mb.items()}
             line["cpu_baseline"] = {k: v for k, v in cpu_arm(args, small, args.cpu_seconds, res_dev["score"]).items()
                                     if k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+    else:
+        line = None
     eng.close()
     if dist is not None:
-        dist.destroy_process_group()
+        dist.barrier()
+        dist.destroy_process_group()       # the application leg below runs without NCCL: the other ranks are gone by then
+    if rank == 0:
+        if not args.no_reads_leg:
+            try:
+                line["reads"] = reads_leg(world)
+            except Exception as ex:          # the application leg must never cost the kernel numbers
+                line["reads"] = {"unavailable": repr(ex)[:200]}
+        print(json.dumps(line))
 
 
 if __name__ == "__main__":
