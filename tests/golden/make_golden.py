@@ -112,6 +112,26 @@ def make_e2e_small():
     print("self lines:", len(lines))
 
 
+def make_e2e_acgt():
+    """ACGT-only reads (2-bit packed sets on the device: the on-device chain + D-SOFT path of the CLI)."""
+    out = os.path.join(HERE, "e2e_acgt")
+    os.makedirs(out, exist_ok=True)
+    rng = np.random.default_rng(11)
+    genome = [synth.random_genome(70000, rng), synth.random_genome(30000, rng)]
+    synth.write_fasta(os.path.join(out, "ref.fasta"), ["g1", "g2_b"], genome)
+    names, reads = synth.sample_reads(genome, 150000, rng, mean=4000, sd=2500, lo=200, hi=12000)
+    synth.write_fasta(os.path.join(out, "reads.fasta"), names, reads)
+    tmp = "/tmp/golden_e2e_acgt"
+    cfgs = {"t320": dict(ma=1, mi=-1, go=-1, ge=-1, ts=320, to=120),
+            "t512": dict(ma=1, mi=-1, go=-1, ge=-1, ts=512, to=192),
+            "t1024": dict(ma=1, mi=-1, go=-1, ge=-1, ts=1024, to=384),
+            "t200_s2": dict(ma=2, mi=-3, go=-5, ge=-2, ts=200, to=60)}
+    for tag, cfg in cfgs.items():
+        lines = run_ref(tmp, os.path.join(out, "ref.fasta"), os.path.join(out, "reads.fasta"), 4, cfg)
+        open(os.path.join(out, f"expected_{tag}.txt"), "w").write("\n".join(lines) + "\n")
+        print("acgt", tag, "lines:", len(lines))
+
+
 def make_dsoft_golden():
     """Candidates of the reference's own SeedPosTable::DSOFT (seed_pos_table.cpp:100-167) for the
     e2e_small reads (both strands) against the e2e_small reference."""
@@ -158,4 +178,5 @@ if __name__ == "__main__":
     O.build(ref=True)
     make_align_random()
     make_e2e_small()
+    make_e2e_acgt()
     make_dsoft_golden()

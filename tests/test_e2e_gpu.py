@@ -103,3 +103,26 @@ def test_reference_gpu_host_code_links_against_library(tmp_path):
         if fn.startswith("darwin.") and fn.endswith(".out"):
             lines += open(os.path.join(wd, fn)).read().splitlines()
     assert sorted(set(lines)) == expected("t320")
+
+
+ACGT = os.path.join(ROOT, "tests", "golden", "e2e_acgt")
+ACGT_CFGS = {"t320": dict(ma=1, mi=-1, go=-1, ge=-1, ts=320, to=120),
+             "t512": dict(ma=1, mi=-1, go=-1, ge=-1, ts=512, to=192),
+             "t1024": dict(ma=1, mi=-1, go=-1, ge=-1, ts=1024, to=384),
+             "t200_s2": dict(ma=2, mi=-3, go=-5, ge=-2, ts=200, to=60)}
+
+
+@pytest.mark.parametrize("tag", sorted(ACGT_CFGS))
+@pytest.mark.parametrize("mode", ["chains", "host_sched"])
+def test_acgt_reads_device_chains_match_cpu_build(tmp_path, tag, mode):
+    """ACGT-only data: sets are 2-bit packed, so the default path is D-SOFT + whole candidate extensions on the
+    GPU (gact_engine_extend).  Both that path and the tile-round-trip scheduler must reproduce the CPU build."""
+    env = {} if mode == "chains" else {"DARWIN_CHAINS": "0"}
+    got, out = run_darwin(str(tmp_path), os.path.join(ACGT, "ref.fasta"), os.path.join(ACGT, "reads.fasta"), 4,
+                          ACGT_CFGS[tag], env=env)
+    exp = open(os.path.join(ACGT, f"expected_{tag}.txt")).read().splitlines()
+    assert got == exp
+    import json
+    import re
+    summ = json.loads(re.search(r"DARWIN_B200_SUMMARY (\{.*\})", out).group(1))
+    assert summ["tiles"] > 0 and summ["cells"] > 0
