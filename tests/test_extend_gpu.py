@@ -6,7 +6,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def make_case(seed, n_reads=40, genome_len=120000, tile=320):
+def make_case(seed, n_reads=26, genome_len=120000, tile=320):
     import synth
     rng = np.random.default_rng(seed)
     genome = [synth.random_genome(genome_len, rng), synth.random_genome(genome_len // 3, rng)]
