@@ -54,6 +54,7 @@ struct SegCtx {
     int lane, seg, sl, segbase;
     uint32_t *rr;            // rr[i]: substitution table of R[i] (LUT) or enc(R[i]) | enc(R[i-1]) << 16
     uint16_t *qs, *rb;       // enc(Q[j]), enc(R[i])
+    uint32_t *wr, *wq;       // the tile's 2-bit packed words as loaded from HBM (reference / query), <= TS/16 + 2 each
     void *dirbase;
     // constants of the biased x16 domain
     int B, KO, KI, KD, ONE, et, match, mismatch, gap_open, gap_extend;
@@ -69,6 +70,8 @@ struct SegCtx {
         rr = reinterpret_cast<uint32_t *>(my);
         qs = reinterpret_cast<uint16_t *>(my + (TS + 2) * 4);
         rb = reinterpret_cast<uint16_t *>(my + (TS + 2) * 6);
+        wr = reinterpret_cast<uint32_t *>(my + (((TS + 2) * 8 + 15) & ~15));
+        wq = wr + (TS / 16 + 2);
         dirbase = gscratch ? (void *)(gscratch + ((size_t)global_warp * TPW + seg) * dir_bytes) : nullptr;
         B = P.s16_bias; Bp = pk16(B);
         match = P.match; mismatch = P.mismatch; gap_open = P.gap_open; gap_extend = P.gap_extend; et = P.et;
@@ -84,17 +87,42 @@ struct SegCtx {
     }
 };
 
-// stage the tile's bases (DP order) into the segment's shared-memory arrays
+// Base x (1-based, DP order) of a tile whose packed words sit in shared memory: word 0 holds base
+// (off & ~15) of the set.
+__device__ __forceinline__ int smem_base(const uint32_t *w, int off_in_word0, int len, int reverse, int x)
+{
+    const int pos = off_in_word0 + (reverse ? (len - x) : (x - 1));
+    const int code = (w[pos >> 4] >> (2 * (pos & 15))) & 3;
+    return (0x54474341u >> (8 * code)) & 0xff;            // "ACGT"
+}
+
+// Stage the tile's bases (DP order) into the segment's shared-memory arrays.  2-bit packed sets are
+// fetched with coalesced 32-bit loads (one word = 16 bases per lane) into shared memory and expanded
+// from there; 8-bit sets are read per base.
 template <int CS, int LANES, bool LUT>
 __device__ __forceinline__ void seg_stage(const SegCtx<CS, LANES> &cx, const SeqSetDev &rset, const SeqSetDev &qset,
                                           long long ref_off, int ref_len, long long query_off, int query_len,
                                           int reverse, int n, int m)
 {
     __syncwarp();
-    if (n > 0 && m > 0) {
+    const bool work = (n > 0 && m > 0);
+    if (work && rset.packed) {
+        const long long w0 = ref_off >> 4;
+        const int nw = (int)(((ref_off + ref_len - 1) >> 4) - w0) + 1;
+        for (int x = cx.sl; x < nw; x += LANES) cx.wr[x] = __ldg(rset.packed + w0 + x);
+    }
+    if (work && qset.packed) {
+        const long long w0 = query_off >> 4;
+        const int nw = (int)(((query_off + query_len - 1) >> 4) - w0) + 1;
+        for (int x = cx.sl; x < nw; x += LANES) cx.wq[x] = __ldg(qset.packed + w0 + x);
+    }
+    __syncwarp();
+    if (work) {
+        const int ro = (int)(ref_off & 15), qo = (int)(query_off & 15);
         for (int x = cx.sl; x <= n + 1; x += LANES) {
             const bool in = (x >= 1 && x <= n);
-            const int base = in ? tile_base(rset, ref_off, ref_len, reverse, x) : 0;
+            const int base = !in ? 0 : rset.packed ? smem_base(cx.wr, ro, ref_len, reverse, x)
+                                                   : tile_base(rset, ref_off, ref_len, reverse, x);
             cx.rb[x] = (uint16_t)(in ? enc_base(base) : SENT_R);
             if (LUT) {
                 const int code = (base == 'A') ? 0 : (base == 'C') ? 1 : (base == 'G') ? 2 : (base == 'T') ? 3 : 4;
@@ -103,11 +131,14 @@ __device__ __forceinline__ void seg_stage(const SegCtx<CS, LANES> &cx, const Seq
                 cx.rr[x] = w;
             }
         }
-        for (int x = cx.sl; x <= m; x += LANES)
-            cx.qs[x] = (x >= 1) ? (uint16_t)enc_base(tile_base(qset, query_off, query_len, reverse, x)) : (uint16_t)SENT_Q;
+        for (int x = cx.sl; x <= m; x += LANES) {
+            const int base = x < 1 ? 0 : qset.packed ? smem_base(cx.wq, qo, query_len, reverse, x)
+                                                     : tile_base(qset, query_off, query_len, reverse, x);
+            cx.qs[x] = (x >= 1) ? (uint16_t)enc_base(base) : (uint16_t)SENT_Q;
+        }
     }
     __syncwarp();
-    if (!LUT && n > 0 && m > 0) {
+    if (!LUT && work) {
         for (int x = cx.sl; x <= n + 1; x += LANES)
             cx.rr[x] = (uint32_t)cx.rb[x] | ((uint32_t)(x >= 1 ? cx.rb[x - 1] : (uint16_t)SENT_R) << 16);
     }
@@ -737,7 +768,7 @@ inline int s16h_make_plan(const gact_params &p, int num_sms, int warps_per_sm, S
     int wl = et / (2 * CS) + 2;
     pl->win_lanes = wl > lanes ? lanes : wl;
     const int TS = CS * 2 * lanes;
-    pl->seq_bytes = (size_t)(((TS + 2) * 8 + 15) & ~15);
+    pl->seq_bytes = (size_t)(((TS + 2) * 8 + 15) & ~15) + (size_t)((2 * (TS / 16 + 2) * 4 + 15) & ~15);
     pl->dir_bytes = s16h_dir_bytes(CS, pl->win_rows, pl->win_lanes);
     int wps = warps_per_sm > 0 ? warps_per_sm : 16;
     const int wps_max = (CS <= 10) ? 16 : 8;
