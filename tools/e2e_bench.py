@@ -46,6 +46,8 @@ def main():
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
     ap.add_argument("--ref-reads", type=int, default=0, help="reads for the reference CPU build arm (0 = skip)")
     ap.add_argument("--seed", type=int, default=3)
+    ap.add_argument("--self-align", action="store_true",
+                    help="config 1 shape: de-novo self alignment (reads.fasta against itself, PBSIM-CLR-like 3 kb reads)")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
 
@@ -62,9 +64,10 @@ def main():
     open(os.path.join(wd, "params.cfg"), "w").write(cfg)
     n_reads, n_bases = len(reads), int(sum(len(r) for r in reads))
 
+    ref_name = "reads.fasta" if args.self_align else "ref.fasta"      # same file name on both sides -> same_file (darwin.cpp:498-503)
     env = dict(os.environ, DARWIN_GPUS=str(args.gpus))
     t0 = time.perf_counter()
-    r = subprocess.run([os.path.join(ROOT, "darwin-gpu_b200", "darwin"), "ref.fasta", "reads.fasta", str(args.threads)],
+    r = subprocess.run([os.path.join(ROOT, "darwin-gpu_b200", "darwin"), ref_name, "reads.fasta", str(args.threads)],
                        cwd=wd, capture_output=True, text=True, env=env)
     wall = time.perf_counter() - t0
     if r.returncode != 0:
@@ -88,10 +91,11 @@ def main():
 
     ref_exe = os.path.join(ROOT, "oracle", "_ref", "darwin_ref")
     if args.ref_reads > 0 and os.path.exists(ref_exe):
-        k = min(args.ref_reads, n_reads)
+        k = n_reads if args.self_align else min(args.ref_reads, n_reads)
         synth.write_fasta(os.path.join(wd, "reads_sub.fasta"), names[:k], reads[:k])
         t0 = time.perf_counter()
-        rr = subprocess.run([ref_exe, "ref.fasta", "reads_sub.fasta", str(args.threads)], cwd=wd, capture_output=True, text=True)
+        ref_args = ["reads.fasta", "reads.fasta"] if args.self_align else ["ref.fasta", "reads_sub.fasta"]
+        rr = subprocess.run([ref_exe, *ref_args, str(args.threads)], cwd=wd, capture_output=True, text=True)
         ref_wall = time.perf_counter() - t0
         ref_lines = collect(wd)
         ref_align = int(re.search(r"Time elapsed \(seed table querying \+ aligning\): (\d+) msec", rr.stdout).group(1)) / 1e3
