@@ -848,6 +848,27 @@ int gact_dsoft_create(gact_dsoft **out, gact_engine *e, const uint32_t *index_ta
     return GACT_OK;
 }
 
+int gact_dsoft_reserve(gact_dsoft *d, int n_queries, int64_t out_cap)
+{
+    if (!d || n_queries < 0 || out_cap < 0) return GACT_ERR_ARG;
+    gact_engine *e = d->e;
+    CU(e, cudaSetDevice(e->device));
+    if ((size_t)n_queries > d->q_cap) {
+        cudaFree(d->d_queries);
+        d->d_queries = nullptr;
+        if (cudaMalloc(&d->d_queries, (size_t)n_queries * sizeof(DsoftQuery)) != cudaSuccess) { cudaGetLastError(); d->q_cap = 0; return fail(e, GACT_ERR_NOMEM, "cudaMalloc(queries) failed"); }
+        d->q_cap = (size_t)n_queries;
+    }
+    if ((size_t)out_cap > d->out_cap || !d->d_out) {
+        cudaFree(d->d_out);
+        d->d_out = nullptr;
+        const size_t want = std::max<size_t>((size_t)out_cap, 1024);
+        if (cudaMalloc(&d->d_out, want * sizeof(DsoftCand)) != cudaSuccess) { cudaGetLastError(); d->out_cap = 0; return fail(e, GACT_ERR_NOMEM, "cudaMalloc(candidates) failed"); }
+        d->out_cap = want;
+    }
+    return GACT_OK;
+}
+
 int gact_dsoft_run(gact_dsoft *d, int n_queries, const int32_t *sets, const int64_t *seq_index,
                    gact_dsoft_cand *out, int64_t out_cap, int64_t *n_out)
 {
@@ -867,18 +888,9 @@ int gact_dsoft_run(gact_dsoft *d, int n_queries, const int32_t *sets, const int6
         q[(size_t)i].len = (int)(hs.starts[(size_t)seq_index[i] + 1] - hs.starts[(size_t)seq_index[i]]);
         q[(size_t)i].set = s;
     }
-    if ((size_t)n_queries > d->q_cap) {
-        cudaFree(d->d_queries);
-        d->d_queries = nullptr;
-        if (cudaMalloc(&d->d_queries, (size_t)n_queries * sizeof(DsoftQuery)) != cudaSuccess) { cudaGetLastError(); d->q_cap = 0; return fail(e, GACT_ERR_NOMEM, "cudaMalloc(queries) failed"); }
-        d->q_cap = (size_t)n_queries;
-    }
-    if ((size_t)out_cap > d->out_cap || !d->d_out) {
-        cudaFree(d->d_out);
-        d->d_out = nullptr;
-        const size_t want = std::max<size_t>((size_t)out_cap, 1024);
-        if (cudaMalloc(&d->d_out, want * sizeof(DsoftCand)) != cudaSuccess) { cudaGetLastError(); d->out_cap = 0; return fail(e, GACT_ERR_NOMEM, "cudaMalloc(candidates) failed"); }
-        d->out_cap = want;
+    {
+        int rr = gact_dsoft_reserve(d, n_queries, out_cap);
+        if (rr) return rr;
     }
     for (int i = 0; i < GACT_MAX_SETS; i++) d->p.sets[i] = e->kp.sets[i];
     cudaStream_t st = e->stream;
@@ -928,6 +940,25 @@ int gact_engine_extend_supported(const gact_engine *e)
     return 1;
 }
 
+int gact_engine_extend_reserve(gact_engine *e, int n)
+{
+    if (!e || n < 0) return GACT_ERR_ARG;
+    CU(e, cudaSetDevice(e->device));
+    if ((size_t)n > e->chain_cap) {
+        if (e->d_chain_calls) cudaFree(e->d_chain_calls);
+        if (e->d_chain_res) cudaFree(e->d_chain_res);
+        e->d_chain_calls = nullptr; e->d_chain_res = nullptr; e->chain_cap = 0;
+        if (cudaMalloc(&e->d_chain_calls, (size_t)n * sizeof(ChainCall)) != cudaSuccess ||
+            cudaMalloc(&e->d_chain_res, (size_t)n * sizeof(ChainResult)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(e, GACT_ERR_NOMEM, "cudaMalloc(chain buffers) failed");
+        }
+        e->chain_cap = (size_t)n;
+    }
+    if (!e->ev_c0) { CU(e, cudaEventCreate(&e->ev_c0)); CU(e, cudaEventCreate(&e->ev_c1)); }
+    return GACT_OK;
+}
+
 int gact_engine_extend(gact_engine *e, int n, const gact_call *calls, gact_alignment *out)
 {
     if (!e || n < 0 || (n > 0 && (!calls || !out))) return GACT_ERR_ARG;
@@ -955,16 +986,9 @@ int gact_engine_extend(gact_engine *e, int n, const gact_call *calls, gact_align
         if (c.ref_pos < 0 || c.query_pos < 0 || c.ref_pos > d.ref_len || c.query_pos > d.query_len)
             return fail(e, GACT_ERR_ARG, "call " + std::to_string(i) + ": anchor outside its sequences");
     }
-    if ((size_t)n > e->chain_cap) {
-        if (e->d_chain_calls) cudaFree(e->d_chain_calls);
-        if (e->d_chain_res) cudaFree(e->d_chain_res);
-        e->d_chain_calls = nullptr; e->d_chain_res = nullptr; e->chain_cap = 0;
-        if (cudaMalloc(&e->d_chain_calls, (size_t)n * sizeof(ChainCall)) != cudaSuccess ||
-            cudaMalloc(&e->d_chain_res, (size_t)n * sizeof(ChainResult)) != cudaSuccess) {
-            cudaGetLastError();
-            return fail(e, GACT_ERR_NOMEM, "cudaMalloc(chain buffers) failed");
-        }
-        e->chain_cap = (size_t)n;
+    {
+        int rr = gact_engine_extend_reserve(e, n);
+        if (rr) return rr;
     }
     if (!e->ev_c0) { CU(e, cudaEventCreate(&e->ev_c0)); CU(e, cudaEventCreate(&e->ev_c1)); }
     cudaStream_t st = e->stream;

@@ -170,6 +170,7 @@ int main(int argc, char **argv)
             upload(GACT_SET_REF, ref.seqs, 0, ref.seqs.size());
             upload(GACT_SET_READS, reads.seqs, S.first_read, S.last_read);
             upload(GACT_SET_READS_RC, rev_reads, S.first_read, S.last_read);
+            if (gact_engine_extend_supported(S.eng)) gact_engine_extend_reserve(S.eng, (int)(8 * (S.last_read - S.first_read) + 1024));
         });
     }
 
@@ -202,6 +203,9 @@ int main(int argc, char **argv)
                                            table->num_minimizers(), cfg.seed_size, (int)cfg.window_size, cfg.bin_size,
                                            table->kmer_max_occurence(), cfg.num_seeds, cfg.threshold, cfg.max_candidates);
                 if (rc) shp->error = std::string("gact_dsoft_create: ") + gact_last_error(shp->eng);
+                // buffers for the timed phase: two queries per read, a few candidates per read
+                const size_t nrs = shp->last_read - shp->first_read;
+                if (!rc) gact_dsoft_reserve(shp->dsoft, (int)(2 * nrs), (int64_t)std::max<size_t>(1024, 8 * nrs));
             });
         }
         for (auto &th : up) th.join();

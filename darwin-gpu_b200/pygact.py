@@ -53,7 +53,7 @@ EXPORTS = [
     "gact_engine_stage", "gact_engine_run_staged", "gact_engine_fetch_staged", "gact_engine_sync",
     "gact_engine_last_kernel_ms", "gact_engine_stats", "gact_engine_reset_stats",
     "gact_engine_set_kernel", "gact_engine_get_kernel", "gact_int_peak",
-    "gact_engine_extend", "gact_engine_extend_supported",
+    "gact_engine_extend", "gact_engine_extend_supported", "gact_engine_extend_reserve", "gact_dsoft_reserve",
     "gact_dsoft_create", "gact_dsoft_destroy", "gact_dsoft_run", "gact_dsoft_last_kernel_ms",
 ]
 

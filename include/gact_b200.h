@@ -224,6 +224,8 @@ typedef struct {
 } gact_alignment;
 
 int gact_engine_extend(gact_engine *e, int n, const gact_call *calls, gact_alignment *out);
+/* Optional: allocate the device buffers for up to n calls now (e.g. before a timed phase). */
+int gact_engine_extend_reserve(gact_engine *e, int n);
 int gact_engine_extend_supported(const gact_engine *e);      /* 1 / 0 */
 
 /* ---- D-SOFT candidate filter on the device (seed_pos_table.cpp:100-167, ntcoding.cpp:155-182) ----
@@ -249,6 +251,8 @@ void gact_dsoft_destroy(gact_dsoft *d);
 int  gact_dsoft_run(gact_dsoft *d, int n_queries, const int32_t *sets, const int64_t *seq_index,
                     gact_dsoft_cand *out, int64_t out_cap, int64_t *n_out);
 double gact_dsoft_last_kernel_ms(const gact_dsoft *d);
+/* Optional: allocate the device buffers for n_queries queries / out_cap candidates now. */
+int  gact_dsoft_reserve(gact_dsoft *d, int n_queries, int64_t out_cap);
 
 /* Integer/DPX issue-rate microbenchmark (the roofline denominator of the DP
  * kernels; MEASURED_PEAKS.json has none).  kind: 0 = IADD3, 1 = VIMNMX3.S32,
