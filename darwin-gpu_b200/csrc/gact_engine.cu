@@ -68,6 +68,7 @@ struct gact_engine {
     uint8_t *d_gscratch = nullptr;
     S16Plan s16;              // packed s16x2 kernel launch plan (s16.ok: usable for these params)
     S16HPlan s16h;            // two-tiles-per-warp mapping of the same kernel (tile_size <= 320)
+    S16HPlan s16h_lat;        // chain kernel, one tile per warp: used when candidates < chain slots (latency bound)
     SeqSetHost sets[GACT_MAX_SETS];
     Slot slots[2];
     int head = 0, tail = 0, inflight = 0;   // async ring
@@ -245,7 +246,8 @@ int plan_launch(gact_engine *e)
     // GACT_S16_HALF=0 disables the two-tiles-per-warp mapping
     const char *hv = getenv("GACT_S16_HALF");
     if (!(hv && atoi(hv) == 0) && mode != 1) {
-        if (s16h_make_plan(e->params, e->num_sms, wps, &e->s16h) != 0)
+        if (s16h_make_plan(e->params, e->num_sms, wps, &e->s16h) != 0 ||
+            s16h_make_plan(e->params, e->num_sms, wps, &e->s16h_lat, true) != 0)
             return fail(e, GACT_ERR_CUDA, "s16h kernel attribute setup failed");
     }
     return s16_make_plan(e->params, e->num_sms, mode, wps, &e->s16) == 0
@@ -497,6 +499,7 @@ void gact_engine_destroy(gact_engine *e)
     if (e->d_gscratch) cudaFree(e->d_gscratch);
     s16_free_plan(&e->s16);
     s16h_free_plan(&e->s16h);
+    s16h_free_plan(&e->s16h_lat);
     if (e->d_chain_calls) cudaFree(e->d_chain_calls);
     if (e->d_chain_res) cudaFree(e->d_chain_res);
     if (e->ev_c0) cudaEventDestroy(e->ev_c0);
@@ -996,7 +999,10 @@ int gact_engine_extend(gact_engine *e, int n, const gact_call *calls, gact_align
     CU(e, cudaMemcpyAsync(e->d_chain_calls, cc.data(), (size_t)n * sizeof(ChainCall), cudaMemcpyHostToDevice, st));
     CU(e, cudaMemsetAsync(s.d_counters, 0, 2 * sizeof(int), st));
     CU(e, cudaEventRecord(e->ev_c0, st));
-    s16h_launch_chain(e->s16h, e->kp, e->d_chain_calls, n, e->d_chain_res, e->params.first_tile_score_threshold,
+    // fewer candidates than chain slots: every chain is resident at once and the longest one sets the
+    // time -> use the one-tile-per-warp mapping with its lower per-tile latency
+    const bool latency_mode = e->s16h_lat.ok && n <= e->s16h_lat.ctas * e->s16h_lat.warps_per_cta && !getenv("GACT_CHAIN_THROUGHPUT");
+    s16h_launch_chain(latency_mode ? e->s16h_lat : e->s16h, e->kp, e->d_chain_calls, n, e->d_chain_res, e->params.first_tile_score_threshold,
                       s.d_counters + 1, st);
     CU(e, cudaGetLastError());
     CU(e, cudaEventRecord(e->ev_c1, st));

@@ -727,6 +727,9 @@ inline s16h_first_fn s16h_pick_first(int CS, int lanes, bool lut)
 }
 inline s16h_chain_fn s16h_pick_chain(int CS, int lanes)
 {
+    // latency variants of the chain kernel: one tile per warp also for tile_size <= 320
+    if (CS == 4 && lanes == 32) return gact_chain_s16h_kernel<4, 32>;
+    if (CS == 5 && lanes == 32) return gact_chain_s16h_kernel<5, 32>;
     s16h_chain_fn f = nullptr;
 #define S16H_X(C, L) f = gact_chain_s16h_kernel<C, L>
     S16H_DISPATCH(CS, lanes, S16H_X);
@@ -736,6 +739,8 @@ inline s16h_chain_fn s16h_pick_chain(int CS, int lanes)
 inline size_t s16h_dir_bytes(int CS, int rows, int lanes)
 {
     switch (CS) {
+        case 4: return DirWinH<4>::bytes(rows, lanes);
+        case 5: return DirWinH<5>::bytes(rows, lanes);
         case 8: return DirWinH<8>::bytes(rows, lanes);
         case 10: return DirWinH<10>::bytes(rows, lanes);
         default: return DirWinH<16>::bytes(rows, lanes);
@@ -749,7 +754,10 @@ inline void s16h_free_plan(S16HPlan *pl)
 }
 
 // Two tiles per warp for tile_size <= 320, one tile per warp up to 1024.
-inline int s16h_make_plan(const gact_params &p, int num_sms, int warps_per_sm, S16HPlan *pl)
+// latency = true: plan for the chain kernel only, one tile per warp at every tile size (lower
+// per-tile latency, about 20 % lower throughput): used when a shard has fewer candidates than the GPU
+// has chain slots, so that the longest read's serial tile chain finishes sooner.
+inline int s16h_make_plan(const gact_params &p, int num_sms, int warps_per_sm, S16HPlan *pl, bool latency = false)
 {
     s16h_free_plan(pl);
     *pl = S16HPlan();
@@ -763,6 +771,10 @@ inline int s16h_make_plan(const gact_params &p, int num_sms, int warps_per_sm, S
     int CS, lanes;
     if (T <= 256) { CS = 8; lanes = 16; } else if (T <= 320) { CS = 10; lanes = 16; }
     else if (T <= 512) { CS = 8; lanes = 32; } else { CS = 16; lanes = 32; }
+    if (latency) {
+        if (T > 320) return 0;                       // already one tile per warp
+        CS = (T <= 256) ? 4 : 5; lanes = 32;
+    }
     pl->CS = CS; pl->lanes = lanes;
     pl->win_rows = (et + 1 < T) ? et + 1 : T;
     int wl = et / (2 * CS) + 2;
@@ -779,7 +791,7 @@ inline int s16h_make_plan(const gact_params &p, int num_sms, int warps_per_sm, S
     pl->smem = (size_t)pl->warps_per_cta * pl->tpw() * pl->seq_bytes;
     const size_t total = (size_t)pl->ctas * pl->warps_per_cta * pl->tpw() * pl->dir_bytes;
     if (cudaMalloc(&pl->d_scratch, total) != cudaSuccess) { cudaGetLastError(); pl->d_scratch = nullptr; return 0; }
-    for (int lut = 0; lut < 2; lut++)
+    for (int lut = 0; lut < 2 && !latency; lut++)
         if (cudaFuncSetAttribute((const void *)s16h_pick(CS, lanes, lut != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)pl->smem) != cudaSuccess ||
             cudaFuncSetAttribute((const void *)s16h_pick_first(CS, lanes, lut != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
