@@ -972,13 +972,26 @@ int gact_engine_extend(gact_engine *e, int n, const gact_call *calls, gact_align
     CU(e, cudaSetDevice(e->device));
     std::vector<ChainCall> cc((size_t)n);
     const SeqSetHost &rs = e->sets[GACT_SET_REF];
+    // longest query first: a chain is a serial run of tiles, so the long ones must start early or they
+    // are still running alone when every other chain slot has drained
+    std::vector<int> perm((size_t)n);
+    for (int i = 0; i < n; i++) perm[(size_t)i] = i;
+    {
+        std::vector<int64_t> qlen((size_t)n, 0);
+        for (int i = 0; i < n; i++) {
+            const gact_call &c = calls[i];
+            if (c.query_set < GACT_MAX_SETS && c.query_seq >= 0 && (size_t)c.query_seq + 1 < e->sets[c.query_set].starts.size())
+                qlen[(size_t)i] = e->sets[c.query_set].starts[(size_t)c.query_seq + 1] - e->sets[c.query_set].starts[(size_t)c.query_seq];
+        }
+        if (!getenv("GACT_CHAIN_NOSORT")) std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return qlen[(size_t)a] > qlen[(size_t)b]; });
+    }
     for (int i = 0; i < n; i++) {
-        const gact_call &c = calls[i];
+        const gact_call &c = calls[perm[(size_t)i]];
         if (c.query_set >= GACT_MAX_SETS || c.ref_seq < 0 || (size_t)c.ref_seq + 1 >= rs.starts.size())
-            return fail(e, GACT_ERR_ARG, "call " + std::to_string(i) + " out of range");
+            return fail(e, GACT_ERR_ARG, "call " + std::to_string(perm[(size_t)i]) + " out of range");
         const SeqSetHost &qs = e->sets[c.query_set];
         if (c.query_seq < 0 || (size_t)c.query_seq + 1 >= qs.starts.size())
-            return fail(e, GACT_ERR_ARG, "call " + std::to_string(i) + " out of range");
+            return fail(e, GACT_ERR_ARG, "call " + std::to_string(perm[(size_t)i]) + " out of range");
         ChainCall &d = cc[(size_t)i];
         d.ref_start = rs.starts[(size_t)c.ref_seq];
         d.query_start = qs.starts[(size_t)c.query_seq];
@@ -987,7 +1000,7 @@ int gact_engine_extend(gact_engine *e, int n, const gact_call *calls, gact_align
         d.ref_pos = c.ref_pos; d.query_pos = c.query_pos;
         d.query_set = c.query_set; d.pad = 0;
         if (c.ref_pos < 0 || c.query_pos < 0 || c.ref_pos > d.ref_len || c.query_pos > d.query_len)
-            return fail(e, GACT_ERR_ARG, "call " + std::to_string(i) + ": anchor outside its sequences");
+            return fail(e, GACT_ERR_ARG, "call " + std::to_string(perm[(size_t)i]) + ": anchor outside its sequences");
     }
     {
         int rr = gact_engine_extend_reserve(e, n);
@@ -1002,8 +1015,13 @@ int gact_engine_extend(gact_engine *e, int n, const gact_call *calls, gact_align
     // fewer candidates than chain slots: every chain is resident at once and the longest one sets the
     // time -> use the one-tile-per-warp mapping with its lower per-tile latency
     const bool latency_mode = e->s16h_lat.ok && n <= e->s16h_lat.ctas * e->s16h_lat.warps_per_cta && !getenv("GACT_CHAIN_THROUGHPUT");
+    // every chain resident in the two-tiles-per-warp mapping: deal the (sorted) chains round-robin over the
+    // CTAs so that the long ones do not share SMs; with more chains than slots the plain in-order claim
+    // measured faster (profiles/r1_chain_order.txt)
+    int deal = (!latency_mode && n <= e->s16h.ctas * e->s16h.warps_per_cta * e->s16h.tpw()) ? 1 : 0;
+    if (getenv("GACT_CHAIN_DEAL")) deal = atoi(getenv("GACT_CHAIN_DEAL"));
     s16h_launch_chain(latency_mode ? e->s16h_lat : e->s16h, e->kp, e->d_chain_calls, n, e->d_chain_res, e->params.first_tile_score_threshold,
-                      s.d_counters + 1, st);
+                      s.d_counters + 1, st, deal);
     CU(e, cudaGetLastError());
     CU(e, cudaEventRecord(e->ev_c1, st));
     std::vector<ChainResult> res((size_t)n);
@@ -1019,7 +1037,7 @@ int gact_engine_extend(gact_engine *e, int n, const gact_call *calls, gact_align
     e->stats.d2h_bytes += (double)n * sizeof(ChainResult);
     for (int i = 0; i < n; i++) {
         const ChainResult &r = res[(size_t)i];
-        gact_alignment &o = out[i];
+        gact_alignment &o = out[perm[(size_t)i]];
         o.ab = r.ab; o.ae = r.ae; o.bb = r.bb; o.be = r.be; o.score = r.score; o.first_tile_score = r.first_tile_score;
         o.n_tiles = r.n_tiles; o.reserved = 0; o.n_cells = r.n_cells;
         e->stats.tiles += (uint64_t)r.n_tiles;

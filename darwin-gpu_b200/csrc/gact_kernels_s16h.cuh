@@ -561,7 +561,7 @@ template <int CS, int LANES>
 __global__ void __launch_bounds__(128, (CS <= 10 ? 3 : 2))
 gact_chain_s16h_kernel(const __grid_constant__ KParams P, const ChainCall *__restrict__ calls, int n_calls,
                        ChainResult *__restrict__ results, int thr, int *counter, size_t seq_bytes,
-                       uint8_t *gscratch, size_t dir_bytes)
+                       uint8_t *gscratch, size_t dir_bytes, int deal)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr unsigned SEGBITS = (LANES == 32) ? 0xffffffffu : ((1u << LANES) - 1u);
@@ -580,6 +580,10 @@ gact_chain_s16h_kernel(const __grid_constant__ KParams P, const ChainCall *__res
     long long n_cells = 0;
     int phase = 2, first_tile = 0, prev_gap = 0, anchor_gap = 0, left_any = 0, adv = 1;
     bool alive = true;                       // false once the queue is empty for this segment
+    bool first_claim = deal != 0;
+    constexpr int SEGS = 32 / LANES;
+    const int lseg = (threadIdx.x >> 5) * SEGS + cx.segbase / LANES;
+    const int n_first = deal ? (int)gridDim.x * (int)(blockDim.x >> 5) * SEGS : 0;   // calls dealt by the fixed first claims
 
     for (;;) {
         // ---- next tile of this segment's candidate (loop heads of gact.cpp:82 and :144) ----
@@ -594,9 +598,18 @@ gact_chain_s16h_kernel(const __grid_constant__ KParams P, const ChainCall *__res
                     r.n_tiles = n_tiles; r.pad = 0; r.n_cells = n_cells;
                     results[call] = r;
                 }
-                int nxt = 0;
-                if (sl == 0) nxt = atomicAdd(counter, 1);
-                nxt = __shfl_sync(segmask, nxt, cx.segbase);
+                // calls arrive longest first.  The first claim of every segment is fixed so that the longest
+                // chains are dealt round-robin over the CTAs (and hence SMs) instead of filling CTA 0 first;
+                // later claims take the next call in order.
+                int nxt = n_calls;
+                if (first_claim) {
+                    first_claim = false;
+                    nxt = lseg * (int)gridDim.x + (int)blockIdx.x;
+                }
+                if (nxt >= n_calls) {
+                    if (sl == 0) nxt = n_first + atomicAdd(counter, 1);
+                    nxt = __shfl_sync(segmask, nxt, cx.segbase);
+                }
                 if (nxt >= n_calls) { alive = false; call = -1; break; }
                 call = nxt;
                 c = calls[call];
@@ -698,7 +711,7 @@ struct S16HPlan {
 typedef void (*s16h_fn)(const KParams, const gact_tile_desc *, const int *, int, const EffLen *, gact_tile_result *,
                         uint32_t *, int, int *, size_t, uint8_t *, size_t);
 typedef void (*s16h_first_fn)(const KParams, const gact_tile_desc *, const int *, int, EffLen *, int *, size_t);
-typedef void (*s16h_chain_fn)(const KParams, const ChainCall *, int, ChainResult *, int, int *, size_t, uint8_t *, size_t);
+typedef void (*s16h_chain_fn)(const KParams, const ChainCall *, int, ChainResult *, int, int *, size_t, uint8_t *, size_t, int);
 
 // (strip width, lanes per tile): T <= 256: (8,16), <= 320: (10,16), <= 512: (8,32), <= 1024: (16,32)
 #define S16H_DISPATCH(CSV, LANESV, EXPR_CS_LANES)                         \
@@ -812,14 +825,14 @@ inline int s16h_grid(const S16HPlan &pl, int n_items)
 }
 
 inline void s16h_launch_chain(const S16HPlan &pl, KParams kp, const ChainCall *calls, int n_calls, ChainResult *results,
-                              int thr, int *counter, cudaStream_t st)
+                              int thr, int *counter, cudaStream_t st, int deal = 1)
 {
     kp.win_rows = pl.win_rows;
     kp.win_lanes = pl.win_lanes;
     kp.s16_bias = pl.bias;
     kp.one = 1;
     s16h_pick_chain(pl.CS, pl.lanes)<<<s16h_grid(pl, n_calls), pl.warps_per_cta * 32, pl.smem, st>>>(
-        kp, calls, n_calls, results, thr, counter, pl.seq_bytes, pl.d_scratch, pl.dir_bytes);
+        kp, calls, n_calls, results, thr, counter, pl.seq_bytes, pl.d_scratch, pl.dir_bytes, deal);
 }
 
 inline void s16h_launch_first(const S16HPlan &pl, KParams kp, const gact_tile_desc *descs, const int *first_list,
