@@ -310,7 +310,7 @@ def main():
         for lo, hi in bounds:
             eng.submit(d[lo:hi])
             pend.append((lo, hi))
-            if len(pend) == 2:
+            if len(pend) == G.MAX_INFLIGHT:
                 a, b = pend.pop(0)
                 eng.wait(e2e_res[a:b], e2e_st[a:b])
         while pend:

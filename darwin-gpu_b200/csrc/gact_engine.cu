@@ -41,7 +41,7 @@ struct Slot {
     int *d_first = nullptr, *h_first = nullptr;
     int *d_order = nullptr, *h_order = nullptr;      // tiles by descending reference length (pairs similar tiles)
     int *d_counters = nullptr;            // [0] first pass, [1] main pass
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr, ev_h2d = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr, ev_h2d = nullptr, ev_fork = nullptr;
     int n = 0, n_first = 0;
     bool busy = false;
     unsigned long long cells = 0;
@@ -54,6 +54,8 @@ struct gact_engine {
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams: descriptor upload / result download overlap the kernels
+    cudaStream_t cs[GACT_MAX_INFLIGHT] = {};         // compute streams of the async slots: the kernel of batch k+1
+                                                     // fills the SMs that the tail of batch k leaves idle
     gact_params params{};
     KParams kp{};
     int max_tiles = 0;
@@ -70,7 +72,7 @@ struct gact_engine {
     S16HPlan s16h;            // two-tiles-per-warp mapping of the same kernel (tile_size <= 320)
     S16HPlan s16h_lat;        // chain kernel, one tile per warp: used when candidates < chain slots (latency bound)
     SeqSetHost sets[GACT_MAX_SETS];
-    Slot slots[2];
+    Slot slots[GACT_MAX_INFLIGHT];
     int head = 0, tail = 0, inflight = 0;   // async ring
     bool staged = false;
     double last_kernel_ms = -1.0;
@@ -153,6 +155,7 @@ void free_slot(Slot &s)
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+    if (s.ev_fork) cudaEventDestroy(s.ev_fork);
     s = Slot();
 }
 
@@ -261,9 +264,9 @@ bool use_s16(const gact_engine *e)
     return e->s16.ok;
 }
 
-int launch_batch(gact_engine *e, Slot &s)
+int launch_batch(gact_engine *e, Slot &s, cudaStream_t st, int scratch_region)
 {
-    cudaStream_t st = e->stream;
+    CU(e, cudaStreamWaitEvent(st, s.ev_h2d, 0));        // descriptors of this batch are on the device
     CU(e, cudaMemsetAsync(s.d_counters, 0, 2 * sizeof(int), st));
     CU(e, cudaEventRecord(s.ev_k0, st));
     const int TS = e->C * 32;
@@ -280,7 +283,7 @@ int launch_batch(gact_engine *e, Slot &s)
     }
     if (use_s16(e) && e->s16h.ok) {
         s16h_launch(e->s16h, e->kp, s.d_descs, s.d_order, s.n, s.d_eff, s.d_results, s.d_states, e->pitch_words,
-                    s.d_counters + 1, st);
+                    s.d_counters + 1, st, scratch_region);
     } else if (use_s16(e)) {
         s16_launch(e->s16, e->kp, s.d_descs, s.n, s.d_eff, s.d_results, s.d_states, e->pitch_words,
                    s.d_counters + 1, st);
@@ -339,7 +342,6 @@ int enqueue(gact_engine *e, Slot &s, int n, const gact_tile_desc *descs)
         CU(e, cudaMemcpyAsync(s.d_first, s.h_first, (size_t)s.n_first * sizeof(int), cudaMemcpyHostToDevice, e->s_h2d));
     CU(e, cudaMemcpyAsync(s.d_order, s.h_order, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, e->s_h2d));
     CU(e, cudaEventRecord(s.ev_h2d, e->s_h2d));
-    CU(e, cudaStreamWaitEvent(e->stream, s.ev_h2d, 0));
     e->stats.h2d_bytes += (double)n * (sizeof(gact_tile_desc) + sizeof(int)) + (double)s.n_first * sizeof(int);
     return GACT_OK;
 }
@@ -449,6 +451,7 @@ int gact_engine_create(gact_engine **out, int device, const gact_params *p, int 
         else { CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->owns_stream = true; }
         CK(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+        for (int k = 0; k < GACT_MAX_INFLIGHT; k++) CK(cudaStreamCreateWithFlags(&e->cs[k], cudaStreamNonBlocking));
 
         const int et = p->tile_size - p->tile_overlap;
         e->pitch_words = (2 * et + 15) / 16 + 1;
@@ -460,7 +463,7 @@ int gact_engine_create(gact_engine **out, int device, const gact_params *p, int 
         rc = plan_launch(e);
         if (rc) { g_create_error = e->err; goto bad; }
 
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < GACT_MAX_INFLIGHT; k++) {
             Slot &s = e->slots[k];
             const size_t n = (size_t)max_tiles;
             CK(cudaMalloc(&s.d_descs, n * sizeof(gact_tile_desc)));
@@ -479,6 +482,7 @@ int gact_engine_create(gact_engine **out, int device, const gact_params *p, int 
             CK(cudaEventCreate(&s.ev_k1));
             CK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
         }
     }
 #undef CK
@@ -494,8 +498,10 @@ void gact_engine_destroy(gact_engine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    for (int k = 0; k < GACT_MAX_INFLIGHT; k++) if (e->cs[k]) cudaStreamSynchronize(e->cs[k]);
+    if (e->s_d2h) cudaStreamSynchronize(e->s_d2h);
     for (int i = 0; i < GACT_MAX_SETS; i++) free_set(e->sets[i]);
-    for (int k = 0; k < 2; k++) free_slot(e->slots[k]);
+    for (int k = 0; k < GACT_MAX_INFLIGHT; k++) free_slot(e->slots[k]);
     if (e->d_gscratch) cudaFree(e->d_gscratch);
     s16_free_plan(&e->s16);
     s16h_free_plan(&e->s16h);
@@ -506,6 +512,7 @@ void gact_engine_destroy(gact_engine *e)
     if (e->ev_c1) cudaEventDestroy(e->ev_c1);
     if (e->s_h2d) { cudaStreamSynchronize(e->s_h2d); cudaStreamDestroy(e->s_h2d); }
     if (e->s_d2h) { cudaStreamSynchronize(e->s_d2h); cudaStreamDestroy(e->s_d2h); }
+    for (int k = 0; k < GACT_MAX_INFLIGHT; k++) if (e->cs[k]) { cudaStreamSynchronize(e->cs[k]); cudaStreamDestroy(e->cs[k]); }
     if (e->owns_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -611,20 +618,27 @@ int gact_engine_submit(gact_engine *e, int n, const gact_tile_desc *descs)
 {
     if (!e) return GACT_ERR_ARG;
     if (e->staged) return fail(e, GACT_ERR_STATE, "submit while a staged batch is pending");
-    if (e->inflight >= 2) return fail(e, GACT_ERR_STATE, "two batches already in flight");
+    if (e->inflight >= GACT_MAX_INFLIGHT) return fail(e, GACT_ERR_STATE, "GACT_MAX_INFLIGHT batches already in flight");
     CU(e, cudaSetDevice(e->device));
     Slot &s = e->slots[e->head];
+    // The two slots launch on their own streams, ordered after the work already enqueued on the
+    // caller's stream.  Kernels that share one scratch area (int32 / one-tile-per-warp variants) stay
+    // on one stream.
+    const bool overlap = use_s16(e) && e->s16h.ok;
+    cudaStream_t st = e->cs[overlap ? e->head : 0];
+    CU(e, cudaEventRecord(s.ev_fork, e->stream));
+    CU(e, cudaStreamWaitEvent(st, s.ev_fork, 0));
     int rc = enqueue(e, s, n, descs);
     if (rc) return rc;
     if (n > 0) {
-        rc = launch_batch(e, s);
+        rc = launch_batch(e, s, st, overlap ? e->head : 0);
         if (rc) return rc;
         rc = download(e, s, true);
         if (rc) return rc;
     }
-    CU(e, cudaEventRecord(s.ev_done, n > 0 ? e->s_d2h : e->stream));
+    CU(e, cudaEventRecord(s.ev_done, n > 0 ? e->s_d2h : st));
     s.busy = true;
-    e->head ^= 1;
+    e->head = (e->head + 1) % GACT_MAX_INFLIGHT;
     e->inflight++;
     return GACT_OK;
 }
@@ -637,7 +651,7 @@ int gact_engine_wait(gact_engine *e, gact_tile_result *results, uint32_t *packed
     Slot &s = e->slots[e->tail];
     int rc = finish(e, s, results, packed_states, true);
     s.busy = false;
-    e->tail ^= 1;
+    e->tail = (e->tail + 1) % GACT_MAX_INFLIGHT;
     e->inflight--;
     return rc;
 }
@@ -653,7 +667,7 @@ int gact_engine_wait_view(gact_engine *e, int *n, const gact_tile_result **resul
     if (results) *results = s.h_results;
     if (packed_states) *packed_states = s.h_states;
     s.busy = false;
-    e->tail ^= 1;
+    e->tail = (e->tail + 1) % GACT_MAX_INFLIGHT;
     e->inflight--;
     return rc;
 }
@@ -669,7 +683,7 @@ int gact_engine_align_tiles(gact_engine *e, int n, const gact_tile_desc *descs,
     int rc = enqueue(e, s, n, descs);
     if (rc) return rc;
     if (n > 0) {
-        rc = launch_batch(e, s);
+        rc = launch_batch(e, s, e->stream, 0);
         if (rc) return rc;
         rc = download(e, s, packed_states != nullptr);
         if (rc) return rc;
@@ -699,7 +713,7 @@ int gact_engine_run_staged(gact_engine *e)
     CU(e, cudaSetDevice(e->device));
     Slot &s = e->slots[0];
     if (s.n == 0) return GACT_OK;
-    int rc = launch_batch(e, s);
+    int rc = launch_batch(e, s, e->stream, 0);
     if (rc) return rc;
     e->stats.tiles += s.n;
     e->stats.cells += s.cells;
@@ -712,6 +726,7 @@ int gact_engine_sync(gact_engine *e)
 {
     if (!e) return GACT_ERR_ARG;
     CU(e, cudaSetDevice(e->device));
+    for (int k = 0; k < GACT_MAX_INFLIGHT; k++) CU(e, cudaStreamSynchronize(e->cs[k]));
     CU(e, cudaStreamSynchronize(e->stream));
     return GACT_OK;
 }

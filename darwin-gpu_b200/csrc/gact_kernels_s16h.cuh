@@ -704,7 +704,8 @@ struct S16HPlan {
     int CS = 0, lanes = 16, win_rows = 0, win_lanes = 0, warps_per_cta = 4, ctas = 0, bias = 0;
     bool lut_ok = false;
     size_t seq_bytes = 0, smem = 0, dir_bytes = 0;
-    uint8_t *d_scratch = nullptr;
+    uint8_t *d_scratch = nullptr;        // GACT_MAX_INFLIGHT regions of scratch_bytes: kernels of consecutive batches may overlap
+    size_t scratch_bytes = 0;
     int tpw() const { return 32 / lanes; }
 };
 
@@ -802,8 +803,8 @@ inline int s16h_make_plan(const gact_params &p, int num_sms, int warps_per_sm, S
     const int c = (wps + 3) / 4;
     pl->ctas = c * num_sms;
     pl->smem = (size_t)pl->warps_per_cta * pl->tpw() * pl->seq_bytes;
-    const size_t total = (size_t)pl->ctas * pl->warps_per_cta * pl->tpw() * pl->dir_bytes;
-    if (cudaMalloc(&pl->d_scratch, total) != cudaSuccess) { cudaGetLastError(); pl->d_scratch = nullptr; return 0; }
+    pl->scratch_bytes = (size_t)pl->ctas * pl->warps_per_cta * pl->tpw() * pl->dir_bytes;
+    if (cudaMalloc(&pl->d_scratch, (latency ? 1 : GACT_MAX_INFLIGHT) * pl->scratch_bytes) != cudaSuccess) { cudaGetLastError(); pl->d_scratch = nullptr; return 0; }
     for (int lut = 0; lut < 2 && !latency; lut++)
         if (cudaFuncSetAttribute((const void *)s16h_pick(CS, lanes, lut != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)pl->smem) != cudaSuccess ||
@@ -848,7 +849,7 @@ inline void s16h_launch_first(const S16HPlan &pl, KParams kp, const gact_tile_de
 
 inline void s16h_launch(const S16HPlan &pl, KParams kp, const gact_tile_desc *descs, const int *order, int n,
                         const EffLen *eff, gact_tile_result *results, uint32_t *states, int pitch_words, int *counter,
-                        cudaStream_t st)
+                        cudaStream_t st, int scratch_region = 0)
 {
     kp.win_rows = pl.win_rows;
     kp.win_lanes = pl.win_lanes;
@@ -857,7 +858,8 @@ inline void s16h_launch(const S16HPlan &pl, KParams kp, const gact_tile_desc *de
     bool lut = pl.lut_ok;
     for (int i = 0; i < GACT_MAX_SETS; i++) if (kp.sets[i].bytes) lut = false;
     s16h_pick(pl.CS, pl.lanes, lut)<<<s16h_grid(pl, n), pl.warps_per_cta * 32, pl.smem, st>>>(
-        kp, descs, order, n, eff, results, states, pitch_words, counter, pl.seq_bytes, pl.d_scratch, pl.dir_bytes);
+        kp, descs, order, n, eff, results, states, pitch_words, counter, pl.seq_bytes,
+        pl.d_scratch + (size_t)scratch_region * pl.scratch_bytes, pl.dir_bytes);
 }
 
 }  // namespace gact

@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(HERE, "libgact_b200.so")
 
 GACT_OK = 0
 SET_REF, SET_READS, SET_READS_RC, SET_AUX = 0, 1, 2, 3
+MAX_INFLIGHT = 3          # GACT_MAX_INFLIGHT: async batches between submit() and wait()
 
 TILE_DESC_DTYPE = np.dtype([("ref_off", "<i8"), ("query_off", "<i8"), ("ref_len", "<i4"),
                             ("query_len", "<i4"), ("ref_set", "u1"), ("query_set", "u1"),

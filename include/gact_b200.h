@@ -69,6 +69,7 @@ typedef struct {
 
 #define GACT_MAX_TILE_SIZE 1024
 #define GACT_MAX_SETS 4
+#define GACT_MAX_INFLIGHT 3      /* async batches between gact_engine_submit() and gact_engine_wait() */
 
 /* Sequence sets held on the device.  A set is one concatenated buffer; tiles
  * address it by base offset.  The three sets the reference path needs
@@ -166,15 +167,19 @@ int gact_engine_max_tiles(const gact_engine *e);
 int gact_engine_align_tiles(gact_engine *e, int n, const gact_tile_desc *descs,
                             gact_tile_result *results, uint32_t *packed_states);
 
-/* Asynchronous pair with two internal slots: submit() returns after queueing
- * the copies and kernels of batch k; wait() blocks for the OLDEST outstanding
- * batch and copies its results out.  At most two batches in flight. */
+/* Asynchronous pair over a ring of GACT_MAX_INFLIGHT internal slots: submit()
+ * returns after queueing the copies and kernels of batch k; wait() blocks for
+ * the OLDEST outstanding batch and copies its results out.  The batches run on
+ * internal streams that start after the work already queued on the engine's
+ * stream; the kernels of consecutive batches may overlap (the next batch fills
+ * the SMs the previous one's last tiles leave idle). */
 int gact_engine_submit(gact_engine *e, int n, const gact_tile_desc *descs);
 int gact_engine_wait(gact_engine *e, gact_tile_result *results, uint32_t *packed_states);
 
 /* Like gact_engine_wait(), but hands out pointers into the engine's pinned result buffers
  * instead of copying (n tiles; states rows gact_engine_states_pitch_words() apart).  The
- * pointers stay valid until the second gact_engine_submit() after this call. */
+ * pointers stay valid for (GACT_MAX_INFLIGHT - batches still in flight when this call returns)
+ * further gact_engine_submit() calls. */
 int gact_engine_wait_view(gact_engine *e, int *n, const gact_tile_result **results,
                           const uint32_t **packed_states);
 

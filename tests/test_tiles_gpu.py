@@ -162,6 +162,16 @@ def test_async_submit_wait_matches_sync(pygact):
             assert (unpack_all(s1, r1["n_states"], 400) == unpack_all(s2, r2["n_states"], 400)).all()
         with pytest.raises(G.GactError):
             eng.wait()
+        # the whole ring in flight (kernels of consecutive batches may overlap on the device), one more is refused
+        assert G.MAX_INFLIGHT == 3
+        for k in range(0, 3000, 1000):
+            eng.submit(d[k:k + 1000])
+        with pytest.raises(G.GactError):
+            eng.submit(d[0:10])
+        ring = [eng.wait() for _ in range(3)]
+        for (r1, s1), (r2, s2) in zip(sync, ring):
+            assert (r1 == r2).all()
+            assert (unpack_all(s1, r1["n_states"], 400) == unpack_all(s2, r2["n_states"], 400)).all()
         eng.stage(d[:512]); eng.run_staged(); eng.run_staged()
         ms = eng.last_kernel_ms()
         r3, s3 = eng.fetch_staged()
