@@ -32,6 +32,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "gact_gcups"
 UNIT = "GCUPS"
+NCU_DRAM_BYTES_PER_TILE = (766.013696e6 + 2.496750e9) / 131072     # see roofline.traffic_note
 OPS_PER_CELL = 17.0          # scalar int32 instructions per DP cell
 TILE, OVERLAP = 320, 120
 SCORES = (1, -1, -1, -1)
@@ -358,7 +359,12 @@ def main():
                 "achieved": achieved, "peak": peak_alu * width,
                 "unit": "G algorithmic int ops/s (17 per DP cell, SURVEY 8d); peak = measured ALU-pipe lane-op rate x cells per lane-op",
                 "frac": achieved / (peak_alu * width),
-                "traffic": None, "ops_per_cell": OPS_PER_CELL, "lane_width": "s16x2" if packed else "s32",
+                "traffic": NCU_DRAM_BYTES_PER_TILE * n if (packed and TILE == 320) else None,
+                "traffic_note": "DRAM bytes per launch = ncu --set full capture of this kernel (131072-tile launch: "
+                                "dram__bytes_read.sum 766 MB + dram__bytes_write.sum 2497 MB, profiles/r1_s16h_tile_kernel_ncu.txt) "
+                                "scaled by tile count; it is the per-warp direction window (22 KB/tile, written once, read by the "
+                                "traceback) spilling from L2, about 0.7 TB/s = 10 % of HBM bandwidth, not the bound",
+                "ops_per_cell": OPS_PER_CELL, "lane_width": "s16x2" if packed else "s32",
                 "peak_alu_lane_ops": peak_alu, "frac_of_int32_roofline": achieved / peak_alu,
                 "gcups_roofline_int32_alu": peak_alu / OPS_PER_CELL, "gcups_roofline_s16x2_alu": 2 * peak_alu / OPS_PER_CELL,
                 "note": "frac can exceed 1: the tagged-max formulation executes ~6 ALU-pipe instructions per cell instead "
