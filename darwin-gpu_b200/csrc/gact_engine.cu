@@ -17,6 +17,7 @@
 #include "gact_kernels_s16.cuh"
 #include "gact_kernels_s16h.cuh"
 #include "dsoft.cuh"
+#include "seed_build.cuh"
 #include <algorithm>
 
 using namespace gact;
@@ -799,6 +800,7 @@ struct gact_dsoft {
     gact_engine *e = nullptr;
     DsoftParams p{};
     uint32_t *d_index = nullptr, *d_pos = nullptr;
+    bool owns_tables = true;          // false: the tables belong to a gact_seed_table
     uint32_t *d_keys = nullptr, *d_touched = nullptr;
     unsigned long long *d_vals = nullptr, *d_count = nullptr;
     int *d_counter = nullptr;
@@ -817,11 +819,45 @@ void gact_dsoft_destroy(gact_dsoft *d)
     if (!d) return;
     cudaSetDevice(d->e->device);
     cudaStreamSynchronize(d->e->stream);
-    cudaFree(d->d_index); cudaFree(d->d_pos); cudaFree(d->d_keys); cudaFree(d->d_touched); cudaFree(d->d_vals);
+    if (d->owns_tables) { cudaFree(d->d_index); cudaFree(d->d_pos); }
+    cudaFree(d->d_keys); cudaFree(d->d_touched); cudaFree(d->d_vals);
     cudaFree(d->d_count); cudaFree(d->d_counter); cudaFree(d->d_queries); cudaFree(d->d_out);
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
     delete d;
+}
+
+// everything of a D-SOFT handle except the seed-position table itself
+static int dsoft_alloc(gact_dsoft **out, gact_engine *e, int kmer_size, int window_size, uint32_t bin_size,
+                       uint32_t kmer_max_occurence, int num_seeds, int threshold, int max_candidates)
+{
+    if (kmer_size < 4 || kmer_size > 15 || window_size < 1 || window_size > 32 || window_size >= kmer_size ||
+        bin_size == 0 || num_seeds < 0 || threshold < 1)
+        return fail(e, GACT_ERR_ARG, "bad D-SOFT parameters");
+    CU(e, cudaSetDevice(e->device));
+    gact_dsoft *d = new (std::nothrow) gact_dsoft();
+    if (!d) return fail(e, GACT_ERR_NOMEM, "host allocation failed");
+    d->e = e;
+    d->owns_tables = false;
+    d->ctas = e->num_sms * 2;
+    const size_t warps = (size_t)d->ctas * 4;
+    // every used seed can touch at most max_occ bins: size the per-warp table for the worst case, load <= 0.5
+    uint64_t need = 2ull * ((uint64_t)num_seeds + 2) * std::max<uint32_t>(kmer_max_occurence, 1u);
+    uint32_t cap = 1024;
+    while (cap < need && cap < (1u << 24)) cap <<= 1;
+    if (cap < need) { delete d; return fail(e, GACT_ERR_ARG, "D-SOFT table would exceed 16M slots per warp"); }
+    bool ok = cudaMalloc(&d->d_keys, warps * cap * 4) == cudaSuccess &&
+              cudaMalloc(&d->d_touched, warps * cap * 4) == cudaSuccess &&
+              cudaMalloc(&d->d_vals, warps * cap * 8) == cudaSuccess &&
+              cudaMalloc(&d->d_count, 8) == cudaSuccess && cudaMalloc(&d->d_counter, 4) == cudaSuccess &&
+              cudaEventCreate(&d->ev0) == cudaSuccess && cudaEventCreate(&d->ev1) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); gact_dsoft_destroy(d); return fail(e, GACT_ERR_NOMEM, "cudaMalloc(D-SOFT tables) failed"); }
+    cudaMemsetAsync(d->d_keys, 0, warps * cap * 4, e->stream);
+    d->p.k = kmer_size; d->p.w = window_size; d->p.bin_size = bin_size; d->p.max_occ = kmer_max_occurence;
+    d->p.num_seeds = num_seeds; d->p.threshold = threshold; d->p.max_candidates = max_candidates;
+    d->p.table_cap = cap;
+    *out = d;
+    return GACT_OK;
 }
 
 int gact_dsoft_create(gact_dsoft **out, gact_engine *e, const uint32_t *index_table, uint64_t index_entries,
@@ -830,38 +866,97 @@ int gact_dsoft_create(gact_dsoft **out, gact_engine *e, const uint32_t *index_ta
 {
     if (!out || !e || !index_table || (!pos_table && n_pos)) return GACT_ERR_ARG;
     *out = nullptr;
-    if (kmer_size < 4 || kmer_size > 15 || window_size < 1 || window_size > 32 || window_size >= kmer_size ||
-        index_entries != ((uint64_t)1 << (2 * kmer_size)) + 1 || bin_size == 0 || num_seeds < 0 || threshold < 1)
+    if (kmer_size < 4 || kmer_size > 15 || index_entries != ((uint64_t)1 << (2 * kmer_size)) + 1)
         return fail(e, GACT_ERR_ARG, "bad D-SOFT parameters");
-    CU(e, cudaSetDevice(e->device));
-    gact_dsoft *d = new (std::nothrow) gact_dsoft();
-    if (!d) return fail(e, GACT_ERR_NOMEM, "host allocation failed");
-    d->e = e;
-    d->ctas = e->num_sms * 2;
-    const size_t warps = (size_t)d->ctas * 4;
-    // every used seed can touch at most max_occ bins: size the per-warp table for the worst case, load <= 0.5
-    uint64_t need = 2ull * ((uint64_t)num_seeds + 2) * std::max<uint32_t>(kmer_max_occurence, 1u);
-    uint32_t cap = 1024;
-    while (cap < need && cap < (1u << 24)) cap <<= 1;
-    if (cap < need) { delete d; return fail(e, GACT_ERR_ARG, "D-SOFT table would exceed 16M slots per warp"); }
-    bool ok = cudaMalloc(&d->d_index, index_entries * 4) == cudaSuccess &&
-              cudaMalloc(&d->d_pos, std::max<uint64_t>(n_pos, 1) * 4) == cudaSuccess &&
-              cudaMalloc(&d->d_keys, warps * cap * 4) == cudaSuccess &&
-              cudaMalloc(&d->d_touched, warps * cap * 4) == cudaSuccess &&
-              cudaMalloc(&d->d_vals, warps * cap * 8) == cudaSuccess &&
-              cudaMalloc(&d->d_count, 8) == cudaSuccess && cudaMalloc(&d->d_counter, 4) == cudaSuccess &&
-              cudaEventCreate(&d->ev0) == cudaSuccess && cudaEventCreate(&d->ev1) == cudaSuccess;
-    if (!ok) { cudaGetLastError(); gact_dsoft_destroy(d); return fail(e, GACT_ERR_NOMEM, "cudaMalloc(D-SOFT tables) failed"); }
+    gact_dsoft *d = nullptr;
+    int rc = dsoft_alloc(&d, e, kmer_size, window_size, bin_size, kmer_max_occurence, num_seeds, threshold, max_candidates);
+    if (rc) return rc;
+    d->owns_tables = true;
+    if (cudaMalloc(&d->d_index, index_entries * 4) != cudaSuccess ||
+        cudaMalloc(&d->d_pos, std::max<uint64_t>(n_pos, 1) * 4) != cudaSuccess) {
+        cudaGetLastError(); gact_dsoft_destroy(d);
+        return fail(e, GACT_ERR_NOMEM, "cudaMalloc(D-SOFT tables) failed");
+    }
     cudaMemcpyAsync(d->d_index, index_table, index_entries * 4, cudaMemcpyHostToDevice, e->stream);
     if (n_pos) cudaMemcpyAsync(d->d_pos, pos_table, n_pos * 4, cudaMemcpyHostToDevice, e->stream);
-    cudaMemsetAsync(d->d_keys, 0, warps * cap * 4, e->stream);
     cudaError_t r = cudaStreamSynchronize(e->stream);
     if (r != cudaSuccess) { gact_dsoft_destroy(d); return fail(e, GACT_ERR_CUDA, std::string("D-SOFT upload: ") + cudaGetErrorString(r)); }
     e->stats.h2d_bytes += (double)(index_entries + n_pos) * 4;
     d->p.index_table = d->d_index; d->p.pos_table = d->d_pos;
-    d->p.k = kmer_size; d->p.w = window_size; d->p.bin_size = bin_size; d->p.max_occ = kmer_max_occurence;
-    d->p.num_seeds = num_seeds; d->p.threshold = threshold; d->p.max_candidates = max_candidates;
-    d->p.table_cap = cap;
+    *out = d;
+    return GACT_OK;
+}
+
+// ---- seed-position table built on the device (seed_build.cuh) -------------------------------
+struct gact_seed_table {
+    gact_engine *e = nullptr;
+    SeedTableDev t;
+};
+
+int gact_seed_table_build(gact_seed_table **out, gact_engine *e, const char *ref, uint32_t ref_len, int kmer_size,
+                          uint32_t seed_occurence_multiple, uint32_t bin_size, uint32_t window_size)
+{
+    if (!out || !e || (!ref && ref_len)) return GACT_ERR_ARG;
+    *out = nullptr;
+    if (e->inflight || e->staged) return fail(e, GACT_ERR_STATE, "seed table build while batches are outstanding");
+    CU(e, cudaSetDevice(e->device));
+    gact_seed_table *t = new (std::nothrow) gact_seed_table();
+    if (!t) return fail(e, GACT_ERR_NOMEM, "host allocation failed");
+    t->e = e;
+    std::string err;
+    const int rc = seed_table_build_device(ref ? ref : "", ref_len, kmer_size, window_size, seed_occurence_multiple, bin_size,
+                                           e->stream, &t->t, &err);
+    if (rc) {
+        delete t;
+        return fail(e, rc == 1 ? GACT_ERR_ARG : rc == 2 ? GACT_ERR_NOMEM : GACT_ERR_CUDA, "seed table: " + err);
+    }
+    e->stats.h2d_bytes += (double)ref_len;
+    *out = t;
+    return GACT_OK;
+}
+
+void gact_seed_table_destroy(gact_seed_table *t)
+{
+    if (!t) return;
+    cudaSetDevice(t->e->device);
+    cudaStreamSynchronize(t->e->stream);
+    seed_table_free(&t->t);
+    delete t;
+}
+
+int gact_seed_table_info(const gact_seed_table *t, uint64_t *index_entries, uint32_t *num_minimizers,
+                         uint32_t *kmer_max_occurence, double *build_ms)
+{
+    if (!t) return GACT_ERR_ARG;
+    if (index_entries) *index_entries = t->t.index_entries;
+    if (num_minimizers) *num_minimizers = t->t.n_pos;
+    if (kmer_max_occurence) *kmer_max_occurence = t->t.max_occ;
+    if (build_ms) *build_ms = t->t.build_ms;
+    return GACT_OK;
+}
+
+int gact_seed_table_download(const gact_seed_table *t, uint32_t *index_table, uint32_t *pos_table)
+{
+    if (!t) return GACT_ERR_ARG;
+    gact_engine *e = t->e;
+    CU(e, cudaSetDevice(e->device));
+    if (index_table) CU(e, cudaMemcpy(index_table, t->t.d_index, t->t.index_entries * 4, cudaMemcpyDeviceToHost));
+    if (pos_table && t->t.n_pos) CU(e, cudaMemcpy(pos_table, t->t.d_pos, (size_t)t->t.n_pos * 4, cudaMemcpyDeviceToHost));
+    return GACT_OK;
+}
+
+int gact_dsoft_create_from_table(gact_dsoft **out, gact_engine *e, const gact_seed_table *t, int num_seeds, int threshold,
+                                 int max_candidates)
+{
+    if (!out || !e || !t) return GACT_ERR_ARG;
+    *out = nullptr;
+    if (t->e->device != e->device) return fail(e, GACT_ERR_ARG, "seed table lives on another device");
+    gact_dsoft *d = nullptr;
+    int rc = dsoft_alloc(&d, e, t->t.k, t->t.w, t->t.bin_size, t->t.max_occ, num_seeds, threshold, max_candidates);
+    if (rc) return rc;
+    d->d_index = t->t.d_index; d->d_pos = t->t.d_pos;      // borrowed: the table must outlive the filter
+    d->p.index_table = d->d_index; d->p.pos_table = d->d_pos;
+    CU(e, cudaStreamSynchronize(e->stream));
     *out = d;
     return GACT_OK;
 }

@@ -55,11 +55,13 @@ struct Shard {
     size_t first_read = 0, last_read = 0;     // [first, last)
     int dsoft_threads = 1;
     SchedulerStats stats;
-    long dsoft_ms = 0, gact_ms = 0;
+    long dsoft_ms = 0, gact_ms = 0, init_ms = 0;
     uint64_t cand_fwd = 0, cand_rev = 0;
     std::string error;
     gact_engine *eng = nullptr;               // created before the align phase (like GPU_init, darwin.cpp:611)
     gact_dsoft *dsoft = nullptr;              // device-side D-SOFT filter (optional)
+    gact_seed_table *seed_table = nullptr;    // seed-position table built on this shard's GPU (optional)
+    double table_kernel_ms = 0.0;
 };
 
 int main(int argc, char **argv)
@@ -80,17 +82,19 @@ int main(int argc, char **argv)
     const bool same_file = (ref_path == reads_path);            // darwin.cpp:498-503
     printf("same_file: %d\n", same_file ? 1 : 0);
 
-    int ndev = gact_device_count();
-    if (ndev <= 0) {
-        fprintf(stderr, "darwin: no CUDA device available (the GACT path has no CPU fallback)\n");
-        return 2;
-    }
-    int want_gpus = ndev;
-    if (const char *e = getenv("DARWIN_GPUS")) want_gpus = std::max(1, std::min(ndev, atoi(e)));
+    // the device query initialises the CUDA driver (hundreds of ms): run it beside the FASTA loading
+    const auto t_prog = Clock::now();
+    int ndev = 0;
+    long devq_ms = 0;
+    std::thread devq([&] { ndev = gact_device_count(); devq_ms = ms_since(t_prog); });
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } devq_guard{devq};   // early error returns
     const int kernel_variant = getenv("DARWIN_KERNEL") ? atoi(getenv("DARWIN_KERNEL")) : 0;
     const bool use_chains = !(getenv("DARWIN_CHAINS") && atoi(getenv("DARWIN_CHAINS")) == 0);
     const bool dsoft_on_gpu = !(getenv("DARWIN_DSOFT") && std::string(getenv("DARWIN_DSOFT")) == "host");
-    printf("Using GPU: %d device(s), CPU threads: %d\n", want_gpus, num_threads);
+    // seed-position table: built on every GPU by default (gact_seed_table_build); DARWIN_SEEDTABLE=host builds it
+    // with the host threads and uploads it (the host D-SOFT path needs the host table in any case)
+    const bool table_on_gpu = dsoft_on_gpu && !(getenv("DARWIN_SEEDTABLE") && std::string(getenv("DARWIN_SEEDTABLE")) == "host");
+    printf("CPU threads: %d\n", num_threads);
     printf("Scores: match = %d, mismatch = %d, gap_open = %d, gap_extend = %d\n", cfg.match, cfg.mismatch, cfg.gap_open, cfg.gap_extend);
     printf("Minimizer window size: %d\n", (int)cfg.window_size);
 
@@ -134,6 +138,15 @@ int main(int argc, char **argv)
     std::cout << "Number of reads: " << num_reads << std::endl;
     std::cout << "Time elapsed (loading reads): " << ms_since(t0) << " msec" << std::endl;
 
+    devq.join();
+    if (ndev <= 0) {
+        fprintf(stderr, "darwin: no CUDA device available (the GACT path has no CPU fallback)\n");
+        return 2;
+    }
+    int want_gpus = ndev;
+    if (const char *e = getenv("DARWIN_GPUS")) want_gpus = std::max(1, std::min(ndev, atoi(e)));
+    printf("Using GPU: %d device(s); CUDA driver initialised after %ld msec\n", want_gpus, devq_ms);
+
     // ---- shards: contiguous read ranges, one per GPU (darwin.cpp:619-629 rule) ----------------
     const int G = (int)std::max<size_t>(1, std::min<size_t>((size_t)want_gpus, std::max<size_t>(num_reads, 1)));
     const size_t per = (num_reads + G - 1) / std::max(G, 1);
@@ -156,6 +169,7 @@ int main(int argc, char **argv)
         Shard *shp = &sh;
         init_threads.emplace_back([&, shp] {
             Shard &S = *shp;
+            const auto t_init = Clock::now();
             int rc = gact_engine_create(&S.eng, S.device, &gp, 1 << 17, nullptr);
             if (rc) { S.error = std::string("gact_engine_create: ") + gact_last_error(nullptr); return; }
             if (kernel_variant) gact_engine_set_kernel(S.eng, kernel_variant);
@@ -171,6 +185,7 @@ int main(int argc, char **argv)
             upload(GACT_SET_READS, reads.seqs, S.first_read, S.last_read);
             upload(GACT_SET_READS_RC, rev_reads, S.first_read, S.last_read);
             if (gact_engine_extend_supported(S.eng)) gact_engine_extend_reserve(S.eng, (int)(8 * (S.last_read - S.first_read) + 1024));
+            S.init_ms = ms_since(t_init);
         });
     }
 
@@ -178,30 +193,45 @@ int main(int argc, char **argv)
     std::cout << "\nConstructing seed position table ...\n";
     t0 = Clock::now();
     SeedTable *table = nullptr;
-    try {
-        table = new SeedTable(ref_string.data(), reference_length, cfg.seed_size, (uint32_t)cfg.seed_occurence_multiple,
-                              cfg.bin_size, cfg.window_size, num_threads);
-    } catch (const std::exception &e) {
-        fprintf(stderr, "seed table: %s\n", e.what());
-        return 1;
+    if (!table_on_gpu) {
+        try {
+            table = new SeedTable(ref_string.data(), reference_length, cfg.seed_size, (uint32_t)cfg.seed_occurence_multiple,
+                                  cfg.bin_size, cfg.window_size, num_threads);
+        } catch (const std::exception &e) {
+            fprintf(stderr, "seed table: %s\n", e.what());
+            return 1;
+        }
+        std::cout << "Time elapsed (seed position table construction): " << ms_since(t0) << " msec" << std::endl;
     }
-    std::cout << "Time elapsed (seed position table construction): " << ms_since(t0) << " msec" << std::endl;
 
     for (auto &th : init_threads) th.join();
-    std::cout << "Time elapsed (GPU init, overlapped with the seed table): " << ms_since(t_gpu) << " msec" << std::endl;
+    std::cout << "Time elapsed (GPU init" << (table_on_gpu ? "" : ", overlapped with the seed table") << "): " << ms_since(t_gpu)
+              << " msec" << std::endl;
+    for (auto &sh : shards) std::cout << "GPU " << sh.device << " init alone (context, engine, sequence upload): " << sh.init_ms << " msec" << std::endl;
     for (auto &sh : shards)
         if (!sh.error.empty()) { fprintf(stderr, "shard %d: %s\n", sh.tid, sh.error.c_str()); return 3; }
 
     if (dsoft_on_gpu) {
-        // the seed-position table goes to every GPU once (index: 4^k + 1 words, positions: one word per minimizer)
+        // every GPU gets the seed-position table once (index: 4^k + 1 words, positions: one word per minimizer):
+        // built there from the reference string, or uploaded from the host builder
         auto t_up = Clock::now();
         std::vector<std::thread> up;
         for (auto &sh : shards) {
             Shard *shp = &sh;
             up.emplace_back([&, shp] {
-                int rc = gact_dsoft_create(&shp->dsoft, shp->eng, table->index_table(), table->index_entries(), table->pos_table(),
+                int rc;
+                if (table_on_gpu) {
+                    rc = gact_seed_table_build(&shp->seed_table, shp->eng, ref_string.data(), reference_length, cfg.seed_size,
+                                               (uint32_t)cfg.seed_occurence_multiple, cfg.bin_size, cfg.window_size);
+                    if (rc) { shp->error = std::string("gact_seed_table_build: ") + gact_last_error(shp->eng); return; }
+                    gact_seed_table_info(shp->seed_table, nullptr, nullptr, nullptr, &shp->table_kernel_ms);
+                    rc = gact_dsoft_create_from_table(&shp->dsoft, shp->eng, shp->seed_table, cfg.num_seeds, cfg.threshold,
+                                                      cfg.max_candidates);
+                } else {
+                    rc = gact_dsoft_create(&shp->dsoft, shp->eng, table->index_table(), table->index_entries(), table->pos_table(),
                                            table->num_minimizers(), cfg.seed_size, (int)cfg.window_size, cfg.bin_size,
                                            table->kmer_max_occurence(), cfg.num_seeds, cfg.threshold, cfg.max_candidates);
+                }
                 if (rc) shp->error = std::string("gact_dsoft_create: ") + gact_last_error(shp->eng);
                 // buffers for the timed phase: two queries per read, a few candidates per read
                 const size_t nrs = shp->last_read - shp->first_read;
@@ -209,7 +239,13 @@ int main(int argc, char **argv)
             });
         }
         for (auto &th : up) th.join();
-        std::cout << "Time elapsed (seed table upload to GPU): " << ms_since(t_up) << " msec" << std::endl;
+        if (table_on_gpu) {
+            std::cout << "Time elapsed (seed position table construction): " << ms_since(t0) << " msec" << std::endl;
+            for (auto &sh : shards)
+                std::cout << "GPU " << sh.device << " seed table build (H2D + kernels): " << sh.table_kernel_ms << " msec" << std::endl;
+        } else {
+            std::cout << "Time elapsed (seed table upload to GPU): " << ms_since(t_up) << " msec" << std::endl;
+        }
         for (auto &sh : shards)
             if (!sh.error.empty()) { fprintf(stderr, "shard %d: %s\n", sh.tid, sh.error.c_str()); return 3; }
     }
@@ -371,10 +407,15 @@ int main(int argc, char **argv)
     const long align_ms = ms_since(t0);
     std::cout << "Time elapsed (seed table querying + aligning): " << align_ms << " msec" << std::endl;
     // GPU_close comes after the timed phase in the reference as well (darwin.cpp:634-642)
+    const auto t_down = Clock::now();
     for (auto &sh : shards) {
         if (sh.dsoft) { gact_dsoft_destroy(sh.dsoft); sh.dsoft = nullptr; }
+        if (sh.seed_table) { gact_seed_table_destroy(sh.seed_table); sh.seed_table = nullptr; }
         if (sh.eng) { gact_engine_destroy(sh.eng); sh.eng = nullptr; }
     }
+
+    std::cout << "Time elapsed (GPU teardown): " << ms_since(t_down) << " msec" << std::endl;
+    std::cout << "Time elapsed (program start to here): " << ms_since(t_prog) << " msec" << std::endl;
 
     int rcode = 0;
     uint64_t tiles = 0, cells = 0;

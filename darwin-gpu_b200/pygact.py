@@ -56,6 +56,8 @@ EXPORTS = [
     "gact_engine_set_kernel", "gact_engine_get_kernel", "gact_int_peak",
     "gact_engine_extend", "gact_engine_extend_supported", "gact_engine_extend_reserve", "gact_dsoft_reserve",
     "gact_dsoft_create", "gact_dsoft_destroy", "gact_dsoft_run", "gact_dsoft_last_kernel_ms",
+    "gact_seed_table_build", "gact_seed_table_destroy", "gact_seed_table_info", "gact_seed_table_download",
+    "gact_dsoft_create_from_table",
 ]
 
 CALL_DTYPE = np.dtype([("ref_seq", "<i4"), ("query_seq", "<i4"), ("ref_pos", "<i4"), ("query_pos", "<i4"),
@@ -138,6 +140,17 @@ def load():
     L.gact_dsoft_run.argtypes = [vp, i32, vp, vp, vp, i64, C.POINTER(i64)]
     L.gact_dsoft_last_kernel_ms.restype = C.c_double
     L.gact_dsoft_last_kernel_ms.argtypes = [vp]
+    L.gact_seed_table_build.restype = i32
+    L.gact_seed_table_build.argtypes = [C.POINTER(vp), vp, C.c_char_p, C.c_uint32, i32, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.gact_seed_table_destroy.restype = None
+    L.gact_seed_table_destroy.argtypes = [vp]
+    L.gact_seed_table_info.restype = i32
+    L.gact_seed_table_info.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                       C.POINTER(C.c_double)]
+    L.gact_seed_table_download.restype = i32
+    L.gact_seed_table_download.argtypes = [vp, vp, vp]
+    L.gact_dsoft_create_from_table.restype = i32
+    L.gact_dsoft_create_from_table.argtypes = [C.POINTER(vp), vp, vp, i32, i32, i32]
     L.gact_int_peak.restype = i32
     L.gact_int_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
     _lib = L
@@ -324,13 +337,46 @@ def align_batch(engine, ref_seqs, query_seqs, reverses, firsts):
     return out
 
 
-class Dsoft:
-    """Device-side D-SOFT filter bound to an engine (seed table arrays come from the host builder)."""
+class SeedTable:
+    """Seed-position table built on the device from the concatenated, bin-padded reference string."""
 
-    def __init__(self, engine, index_ptr, index_entries, pos_ptr, n_pos, kmer_size=14, window_size=4, bin_size=64,
-                 max_occ=32, num_seeds=800, threshold=21, max_candidates=1000000):
+    def __init__(self, engine, ref_bytes, kmer_size=14, seed_occurence_multiple=32, bin_size=64, window_size=4):
         self.eng = engine
         self.h = C.c_void_p()
+        rc = engine.L.gact_seed_table_build(C.byref(self.h), engine.h, ref_bytes, len(ref_bytes), kmer_size,
+                                            seed_occurence_multiple, bin_size, window_size)
+        engine._ck(rc, "gact_seed_table_build")
+        ie, npos, mo, ms = C.c_uint64(), C.c_uint32(), C.c_uint32(), C.c_double()
+        engine._ck(engine.L.gact_seed_table_info(self.h, C.byref(ie), C.byref(npos), C.byref(mo), C.byref(ms)),
+                   "gact_seed_table_info")
+        self.index_entries, self.num_minimizers, self.max_occ, self.build_ms = ie.value, npos.value, mo.value, ms.value
+
+    def download(self):
+        index = np.zeros(self.index_entries, dtype=np.uint32)
+        pos = np.zeros(max(self.num_minimizers, 1), dtype=np.uint32)
+        self.eng._ck(self.eng.L.gact_seed_table_download(self.h, index.ctypes.data, pos.ctypes.data),
+                     "gact_seed_table_download")
+        return index, pos[:self.num_minimizers]
+
+    def close(self):
+        if self.h:
+            self.eng.L.gact_seed_table_destroy(self.h)
+            self.h = None
+
+
+class Dsoft:
+    """Device-side D-SOFT filter bound to an engine.  The seed table comes either from the host builder
+    (index_ptr / pos_ptr host arrays) or from a SeedTable built on the device (table=...)."""
+
+    def __init__(self, engine, index_ptr=None, index_entries=0, pos_ptr=None, n_pos=0, kmer_size=14, window_size=4,
+                 bin_size=64, max_occ=32, num_seeds=800, threshold=21, max_candidates=1000000, table=None):
+        self.eng = engine
+        self.h = C.c_void_p()
+        if table is not None:
+            rc = engine.L.gact_dsoft_create_from_table(C.byref(self.h), engine.h, table.h, num_seeds, threshold,
+                                                       max_candidates)
+            engine._ck(rc, "gact_dsoft_create_from_table")
+            return
         rc = engine.L.gact_dsoft_create(C.byref(self.h), engine.h, index_ptr, index_entries, pos_ptr, n_pos,
                                         kmer_size, window_size, bin_size, max_occ, num_seeds, threshold, max_candidates)
         engine._ck(rc, "gact_dsoft_create")

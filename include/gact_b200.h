@@ -251,6 +251,23 @@ int  gact_dsoft_create(gact_dsoft **out, gact_engine *e, const uint32_t *index_t
                        uint32_t bin_size, uint32_t kmer_max_occurence, int num_seeds, int threshold,
                        int max_candidates);
 void gact_dsoft_destroy(gact_dsoft *d);
+
+/* Seed-position table built on the device: replaces the SeedPosTable constructor
+ * (seed_pos_table.cpp:46-98: SeqToTwoBit ntcoding.cpp:87-103, TwoBitToMinimizers ntcoding.cpp:126-153,
+ * sort, index fill).  ref is the HOST string darwin.cpp:530-543 builds: every reference sequence
+ * padded with 'N' to a multiple of bin_size, concatenated.  The tables stay in device memory;
+ * gact_dsoft_create_from_table() borrows them (destroy the filter before the table),
+ * gact_seed_table_download() copies them out (index_table: 4^k + 1 words, pos_table: num_minimizers words;
+ * either may be NULL). */
+typedef struct gact_seed_table gact_seed_table;
+int  gact_seed_table_build(gact_seed_table **out, gact_engine *e, const char *ref, uint32_t ref_len, int kmer_size,
+                           uint32_t seed_occurence_multiple, uint32_t bin_size, uint32_t window_size);
+void gact_seed_table_destroy(gact_seed_table *t);
+int  gact_seed_table_info(const gact_seed_table *t, uint64_t *index_entries, uint32_t *num_minimizers,
+                          uint32_t *kmer_max_occurence, double *build_ms);
+int  gact_seed_table_download(const gact_seed_table *t, uint32_t *index_table, uint32_t *pos_table);
+int  gact_dsoft_create_from_table(gact_dsoft **out, gact_engine *e, const gact_seed_table *t, int num_seeds,
+                                  int threshold, int max_candidates);
 /* queries: (set, sequence index inside the set) pairs.  Returns GACT_ERR_NOMEM with *n_out set to the
  * required capacity when out_cap is too small. */
 int  gact_dsoft_run(gact_dsoft *d, int n_queries, const int32_t *sets, const int64_t *seq_index,

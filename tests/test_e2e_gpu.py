@@ -63,10 +63,10 @@ CFGS = {"t320": dict(ma=1, mi=-1, go=-1, ge=-1, ts=320, to=120),
 
 
 @pytest.mark.parametrize("tag", sorted(CFGS))
-@pytest.mark.parametrize("mode", ["default", "int32", "host_sched", "host_dsoft"])
+@pytest.mark.parametrize("mode", ["default", "int32", "host_sched", "host_dsoft", "host_table"])
 def test_reads_vs_reference_matches_cpu_build(tmp_path, tag, mode):
     env = {"default": {}, "int32": {"DARWIN_KERNEL": "1"}, "host_sched": {"DARWIN_CHAINS": "0"},
-           "host_dsoft": {"DARWIN_DSOFT": "host", "DARWIN_CHAINS": "0"}}[mode]
+           "host_dsoft": {"DARWIN_DSOFT": "host", "DARWIN_CHAINS": "0"}, "host_table": {"DARWIN_SEEDTABLE": "host"}}[mode]
     got, out = run_darwin(str(tmp_path), os.path.join(GOLD, "ref.fasta"), os.path.join(GOLD, "reads.fasta"), 4,
                           CFGS[tag], env=env)
     assert got == expected(tag)

@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--self-align", action="store_true",
                     help="config 1 shape: de-novo self alignment (reads.fasta against itself, PBSIM-CLR-like 3 kb reads)")
     ap.add_argument("--out", default="")
+    ap.add_argument("--show-stdout", action="store_true", help="print the timing lines of the darwin run")
     args = ap.parse_args()
 
     wd = tempfile.mkdtemp(prefix="darwin_e2e_")
@@ -74,14 +75,18 @@ def main():
         print(r.stdout[-2000:], r.stderr[-2000:])
         raise SystemExit("darwin failed")
     ours = collect(wd)
+    if args.show_stdout:
+        print("\n".join(ln for ln in r.stdout.splitlines() if re.search(r"Time elapsed|init|build|driver", ln)), f"\nwall {wall:.3f} s")
     summ = json.loads(re.search(r"DARWIN_B200_SUMMARY (\{.*\})", r.stdout).group(1))
     phase = {k: int(v) for k, v in re.findall(r"Time elapsed \(([^)]*)\): (\d+) msec", r.stdout)}
     seeds_ms = [int(x) for x in re.findall(r"Time finding seeds: (\d+) msec", r.stdout)]
+    init_ms = [int(x) for x in re.findall(r"init alone[^:]*: (\d+) msec", r.stdout)]
+    table_ms = [float(x) for x in re.findall(r"seed table build[^:]*: ([\d.]+) msec", r.stdout)]
     align_s = summ["align_phase_ms"] / 1e3
     res = {"workload": {"ref_mbp": args.ref_mbp, "reads": n_reads, "read_bases": n_bases, "tile_size": args.tile,
                         "tile_overlap": args.overlap, "seed": args.seed},
            "gpus": args.gpus, "host_threads": args.threads,
-           "ours": {"wall_s": wall, "phases_ms": phase, "dsoft_ms_per_shard": seeds_ms, "summary": summ,
+           "ours": {"wall_s": wall, "phases_ms": phase, "dsoft_ms_per_shard": seeds_ms, "gpu_init_alone_ms": init_ms, "gpu_seed_table_build_ms": table_ms, "summary": summ,
                     "reads_per_s_align_phase": n_reads / align_s,
                     "reads_per_s_gact_only": n_reads / max(summ["gact_sched_ms"] / 1e3, 1e-9),
                     "gcups_align_phase": summ["cells"] / align_s / 1e9,
