@@ -19,6 +19,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "darwin-gpu_b200"))
 import numpy as np  # noqa: E402
 import synth  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import accuracy_report  # noqa: E402
 
 PARAMS = open(os.path.join(ROOT, "darwin-gpu_b200", "params.cfg")).read()
 
@@ -93,6 +95,12 @@ def main():
                     "gcups_gact_sched": summ["cells"] / max(summ["gact_sched_ms"] / 1e3, 1e-9) / 1e9,
                     "gcups_kernel": summ["cells"] / max(summ["gact_kernel_ms"] / 1e3, 1e-9) / 1e9,
                     "overlap_lines": len(ours), "unique_lines": len(set(ours))}}
+
+    if args.self_align:
+        # accuracy of the de-novo overlaps against the simulated read positions (reference: measure_sensitivity_PBSIM.py)
+        with open(os.path.join(wd, "out.darwin"), "w") as f:
+            f.write("".join(ln + "\n" for ln in sorted(set(ours))))
+        res["ours"]["accuracy"] = accuracy_report.report(os.path.join(wd, "reads.fasta"), os.path.join(wd, "out.darwin"))
 
     ref_exe = os.path.join(ROOT, "oracle", "_ref", "darwin_ref")
     if args.ref_reads > 0 and os.path.exists(ref_exe):
