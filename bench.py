@@ -301,7 +301,16 @@ def main():
 
     # ---- leg 2: end to end through the C ABI with host buffers (e2e) ----------------------
     chunk = min(args.chunk, n)
-    bounds = [(lo, min(lo + chunk, n)) for lo in range(0, n, chunk)]
+    # pipeline ramp: a quarter- and a half-size batch at both ends, so the first kernel starts after a short upload
+    # and only a short download + copy-out is left after the last one
+    sizes = [chunk // 4, chunk // 2] if n >= 4 * chunk and chunk >= 4096 else []
+    mid = n - 2 * sum(sizes)
+    sizes = sizes + [chunk] * (mid // chunk) + ([mid % chunk] if mid % chunk else []) + sizes[::-1]
+    bounds, lo = [], 0
+    for sz in sizes:
+        bounds.append((lo, lo + sz))
+        lo += sz
+    assert lo == n
 
     e2e_res = np.zeros(n, dtype=G.TILE_RESULT_DTYPE)          # caller-owned host result buffers
     e2e_st = np.zeros((n, eng.pitch), dtype=np.uint32)
@@ -382,7 +391,8 @@ def main():
                 "gcups_per_gpu": gcups / world,
                 "tiles_per_s": n * world * args.steps / (dev_ms_max * 1e-3),
                 "e2e": {"value": e2e_gcups, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms_max / args.steps, "api": "gact_engine_submit/wait, chunks of %d" % chunk},
+                        "ms_per_step": e2e_ms_max / args.steps, "api": "gact_engine_submit/wait, %d batches of up to %d tiles (quarter/half-size batches at both ends), "
+                               "%d in flight" % (len(bounds), chunk, G.MAX_INFLIGHT)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
         if world == 1 and not args.no_cpu_baseline:
             small = {k: (v[:1 << 15] if k not in ("ref", "query") else v) for k, v in mb.items()}
