@@ -315,6 +315,21 @@ __device__ __forceinline__ SegTrace seg_traceback(const SegCtx<CS, LANES> &cx, c
     int state = (work && v > 0) ? (dw.load(i, j) >> 2) : 0;
     bool act = (state != 0);
     while (__any_sync(FULL, act)) {
+        // one gap column (if the segment is in I or D), then the M run that follows it
+        if (act && state != 3) {
+            const int code = dw.load(i, j);
+            const bool open = (state == 2) ? (code & 2) : (code & 1);
+            if (EMIT && sl == 0) stbuf[cnt] = (uint8_t)state;
+            if (cnt == 0) first_gap = 1;
+            cnt++;
+            v -= open ? go : ge;
+            col += pg ? ge : go;
+            pg = 1;
+            if (state == 2) { i--; ri--; } else { j--; rj--; }
+            state = open ? 3 : state;
+            if (i <= 0 || j <= 0) state = 0;
+            act = (state != 0 && ri > 0 && rj > 0);          // the early-terminate test precedes every push (align.cpp:205-207)
+        }
         const bool inM = act && state == 3;
         const int it = i - sl, jt = j - sl;
         const bool inb = inM && it >= i0 && jt >= j0;
@@ -338,18 +353,6 @@ __device__ __forceinline__ SegTrace seg_traceback(const SegCtx<CS, LANES> &cx, c
             if (L > 0) pg = 0;
             i -= L; j -= L;
             state = (i >= i0 && j >= j0 && v > 0) ? (codeL >> 2) : 0;
-        } else if (act) {
-            const int code = dw.load(i, j);
-            const bool open = (state == 2) ? (code & 2) : (code & 1);
-            if (EMIT && sl == 0) stbuf[cnt] = (uint8_t)state;
-            if (cnt == 0) first_gap = 1;
-            cnt++;
-            v -= open ? go : ge;
-            col += pg ? ge : go;
-            pg = 1;
-            if (state == 2) { i--; ri--; } else { j--; rj--; }
-            state = open ? 3 : state;
-            if (i <= 0 || j <= 0) state = 0;
         }
         act = (state != 0 && ri > 0 && rj > 0);
     }
