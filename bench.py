@@ -32,7 +32,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "gact_gcups"
 UNIT = "GCUPS"
-NCU_DRAM_BYTES_PER_TILE = (766.013696e6 + 2.496750e9) / 131072     # see roofline.traffic_note
+NCU_DRAM_BYTES_PER_TILE = (705.809152e6 + 2.405678e9) / 131072     # see roofline.traffic_note
 OPS_PER_CELL = 17.0          # scalar int32 instructions per DP cell
 TILE, OVERLAP = 320, 120
 SCORES = (1, -1, -1, -1)
@@ -370,14 +370,14 @@ def main():
                 "frac": achieved / (peak_alu * width),
                 "traffic": NCU_DRAM_BYTES_PER_TILE * n if (packed and TILE == 320) else None,
                 "traffic_note": "DRAM bytes per launch = ncu --set full capture of this kernel (131072-tile launch: "
-                                "dram__bytes_read.sum 766 MB + dram__bytes_write.sum 2497 MB, profiles/r1_s16h_tile_kernel_ncu.txt) "
+                                "dram__bytes_read.sum 706 MB + dram__bytes_write.sum 2406 MB, profiles/r1_s16h_tile_kernel_ncu.txt) "
                                 "scaled by tile count; it is the per-warp direction window (22 KB/tile, written once, read by the "
                                 "traceback) spilling from L2, about 0.7 TB/s = 10 % of HBM bandwidth, not the bound",
                 "ops_per_cell": OPS_PER_CELL, "lane_width": "s16x2" if packed else "s32",
                 "peak_alu_lane_ops": peak_alu, "frac_of_int32_roofline": achieved / peak_alu,
                 "gcups_roofline_int32_alu": peak_alu / OPS_PER_CELL, "gcups_roofline_s16x2_alu": 2 * peak_alu / OPS_PER_CELL,
                 "note": "frac can exceed 1: the tagged-max formulation executes ~6 ALU-pipe instructions per cell instead "
-                        "of the 17 (8.5 packed) the roofline model assumes; ncu of the same kernel: ALU pipe 85 % busy "
+                        "of the 17 (8.5 packed) the roofline model assumes; ncu of the same kernel: ALU pipe 86 % busy, issue slots 67 % "
                         "(profiles/r1_s16h_tile_kernel_ncu.txt)",
                 "peak_alu_fma_mix": peak_mix, "peak_source": "gact_int_peak (own microbenchmark, measured in this run)",
                 "kernel_ms": kernel_ms,
