@@ -154,6 +154,9 @@ dsoft_kernel(const __grid_constant__ DsoftParams P, const DsoftQuery *__restrict
                 b1 = __ldg(P.index_table + m);
             }
             const bool ok = emit && (b1 - b0 <= P.max_occ);
+            // most buckets hold one hit: fetch every bucket's first hit now, all lanes at once, so that the
+            // seed-after-seed loop below does not wait for one more dependent load per seed
+            const uint32_t hit0 = (ok && b1 > b0) ? __ldg(P.pos_table + b0) : 0u;
             const unsigned okmask = __ballot_sync(FULL, ok);
             const int rank = __popc(okmask & ((1u << lane) - 1u));
             // seed budget: the j-th usable minimizer (0-based, over the whole query) is used iff j <= N;
@@ -170,9 +173,12 @@ dsoft_kernel(const __grid_constant__ DsoftParams P, const DsoftQuery *__restrict
                 const uint32_t hb = __shfl_sync(FULL, b0, src), he = __shfl_sync(FULL, b1, src);
                 const uint32_t offset = (uint32_t)(base + src);
                 bool stop_bucket = false;
+                const uint32_t first_hit = __shfl_sync(FULL, hit0, src);
                 for (uint32_t j0 = hb; j0 < he && !stop_bucket; j0 += 32) {
                     const uint32_t j = j0 + lane;
-                    const uint32_t hit = (j < he) ? __ldg(P.pos_table + j) : 0u;
+                    uint32_t hit = 0u;
+                    if (he - hb == 1) hit = first_hit;                    // (only lane 0's copy is read below)
+                    else if (j < he) hit = __ldg(P.pos_table + j);
                     const int cnt = min(32u, he - j0);
                     for (int x = 0; x < cnt; x++) {
                         const uint32_t ht = __shfl_sync(FULL, hit, x);

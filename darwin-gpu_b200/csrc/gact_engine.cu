@@ -839,13 +839,18 @@ static int dsoft_alloc(gact_dsoft **out, gact_engine *e, int kmer_size, int wind
     if (!d) return fail(e, GACT_ERR_NOMEM, "host allocation failed");
     d->e = e;
     d->owns_tables = false;
-    d->ctas = e->num_sms * 2;
-    const size_t warps = (size_t)d->ctas * 4;
     // every used seed can touch at most max_occ bins: size the per-warp table for the worst case, load <= 0.5
     uint64_t need = 2ull * ((uint64_t)num_seeds + 2) * std::max<uint32_t>(kmer_max_occurence, 1u);
     uint32_t cap = 1024;
     while (cap < need && cap < (1u << 24)) cap <<= 1;
     if (cap < need) { delete d; return fail(e, GACT_ERR_ARG, "D-SOFT table would exceed 16M slots per warp"); }
+    // The filter is bound by dependent memory latency (bucket -> hits -> bin slot, seed after seed), so it wants
+    // as many strands in flight as fit: up to 32 warps per SM while the per-warp tables stay under 8 GiB,
+    // never fewer than 8 warps per SM.
+    int ctas_per_sm = 8;
+    while (ctas_per_sm > 2 && (uint64_t)e->num_sms * ctas_per_sm * 4 * cap * 16ull > (8ull << 30)) ctas_per_sm--;
+    d->ctas = e->num_sms * ctas_per_sm;
+    const size_t warps = (size_t)d->ctas * 4;
     bool ok = cudaMalloc(&d->d_keys, warps * cap * 4) == cudaSuccess &&
               cudaMalloc(&d->d_touched, warps * cap * 4) == cudaSuccess &&
               cudaMalloc(&d->d_vals, warps * cap * 8) == cudaSuccess &&
