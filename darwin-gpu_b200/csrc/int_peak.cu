@@ -75,6 +75,53 @@ int run(int device, double *gops)
     return GACT_OK;
 }
 
+// latency: one warp, one dependent chain of the instruction; ns per instruction
+template <int KIND>
+__global__ void __launch_bounds__(32) lat_kernel(int *out, int iters)
+{
+    const int a = out[1], b = out[2];
+    int v = threadIdx.x;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 64; u++) {
+            if (KIND == 2) v = __viaddmax_s32(v, a, b);
+            if (KIND == 3) v = __vimax3_s16x2(v, a, b);
+            if (KIND == 4) v = __viaddmax_s16x2(v, a, b);
+            if (KIND == 5) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v) : "r"(a), "r"(b));
+            if (KIND == 6) asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(v) : "r"(a), "r"(b));
+            if (KIND == 10) v = __byte_perm(v, a, b);
+            if (KIND == 12) v = __shfl_up_sync(0xffffffffu, v, 1);
+            if (KIND == 13) { v = __viaddmax_s16x2(v, a, b); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v) : "r"(a), "r"(b)); }   // the D chain of the DP
+        }
+    }
+    if (v == 0x7fffffff) out[0] = v;
+}
+
+template <int KIND>
+int run_lat(int device, double *ns)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return GACT_ERR_CUDA;
+    int *d = nullptr;
+    if (cudaMalloc(&d, 16) != cudaSuccess) return GACT_ERR_NOMEM;
+    { const int init[4] = {0, 3, -7, 0}; cudaMemcpy(d, init, 16, cudaMemcpyHostToDevice); }
+    const int iters = 4000;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        lat_kernel<KIND><<<1, 32>>>(d, iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return GACT_ERR_CUDA; }
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *ns = (double)best * 1e6 / ((double)iters * 64 * (KIND == 13 ? 2 : 1));
+    return GACT_OK;
+}
+
 }  // namespace
 
 extern "C" int gact_int_peak(int device, int kind, double *gops_out)
@@ -94,6 +141,15 @@ extern "C" int gact_int_peak(int device, int kind, double *gops_out)
         case 10: return run<10>(device, gops_out);
         case 11: return run<11>(device, gops_out);
         case 12: return run<12>(device, gops_out);
+        // 100 + kind: latency of a dependent chain of that instruction, nanoseconds per instruction
+        case 102: return run_lat<2>(device, gops_out);
+        case 103: return run_lat<3>(device, gops_out);
+        case 104: return run_lat<4>(device, gops_out);
+        case 105: return run_lat<5>(device, gops_out);
+        case 106: return run_lat<6>(device, gops_out);
+        case 110: return run_lat<10>(device, gops_out);
+        case 112: return run_lat<12>(device, gops_out);
+        case 113: return run_lat<13>(device, gops_out);
         default: return GACT_ERR_ARG;
     }
 }

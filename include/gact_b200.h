@@ -281,7 +281,9 @@ int  gact_dsoft_reserve(gact_dsoft *d, int n_queries, int64_t out_cap);
  * 2 = VIADDMNMX.S32, 3 = VIMNMX3.S16x2, 4 = VIADDMNMX.S16x2, 5 = LOP3,
  * 6 = IMAD, 7 = 1:1 VIADDMNMX:IMAD mix, 8 = HSET2, 9 = VIADD.16x2, 10 = PRMT,
  * 11 = 1:1 VIMNMX3.S16x2:HSET2 mix, 12 = SHFL.  Writes giga lane-operations
- * per second (one per thread per instruction). */
+ * per second (one per thread per instruction).  kind 100 + k (k = 2, 3, 4, 5, 6, 10, 12; 113 = the
+ * VIADDMNMX.S16x2 + LOP3 pair of the DP's D chain): latency of a dependent chain of that instruction on one
+ * warp, written as nanoseconds per instruction. */
 int gact_int_peak(int device, int kind, double *gops_out);
 
 #ifdef __cplusplus
