@@ -377,11 +377,24 @@ int main(int argc, char **argv)
             const long t_sched = ms_since(tg);
             // the engine is torn down after the output is written (outside the per-shard critical path)
 
-            for (size_t k = 0; k < calls.size(); k++) {
-                const GactCall &c = calls[k];
-                const size_t read_id = sh.first_read + (size_t)c.query_id;
-                if (!(same_file && (size_t)c.ref_id == read_id) && aln[k].score > 0)        // gact.cpp:213
-                    fout << format_overlap(ref.names[c.ref_id], reads.names[read_id], aln[k], c.complement != 0);
+            // format in parallel chunks (same line order as the sequential loop), one write per chunk
+            {
+                const int parts = std::max(1, std::min(sh.dsoft_threads, (int)(calls.size() / 512) + 1));
+                std::vector<std::string> text((size_t)parts);
+                std::vector<std::thread> fmt;
+                for (int p = 0; p < parts; p++) fmt.emplace_back([&, p] {
+                    const size_t a = calls.size() * (size_t)p / parts, b = calls.size() * (size_t)(p + 1) / parts;
+                    std::string &out = text[(size_t)p];
+                    out.reserve((b - a) * 112);
+                    for (size_t k = a; k < b; k++) {
+                        const GactCall &c = calls[k];
+                        const size_t read_id = sh.first_read + (size_t)c.query_id;
+                        if (!(same_file && (size_t)c.ref_id == read_id) && aln[k].score > 0)        // gact.cpp:213
+                            out += format_overlap(ref.names[c.ref_id], reads.names[read_id], aln[k], c.complement != 0);
+                    }
+                });
+                for (auto &t : fmt) t.join();
+                for (auto &t : text) fout.write(t.data(), (std::streamsize)t.size());
             }
             fout.close();
             sh.gact_ms = ms_since(tg);
