@@ -119,6 +119,29 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
+def usable_cores():
+    """Host cores this process may really use: affinity mask and cgroup CPU quota, not just the machine's count
+    (a thread pool wider than the quota gets throttled in bursts, which shows up as tens of ms of jitter)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return n
+
+
 def make_batch(n_tiles, seed):
     import synth
     return synth.tile_microbatch(n_tiles, tile_size=TILE, seed=seed)
@@ -128,7 +151,7 @@ def cpu_arm(args, mb, seconds, gpu_scores=None):
     """Reference CPU AlignWithBT (oracle/_ref) or the oracle port, all host threads, bounded sample."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     n = len(mb["ref_off"])
     od = np.zeros(n, dtype=O.TILE_DESC_DTYPE)
     for k in ("ref_off", "query_off", "ref_len", "query_len", "reverse", "first"):
@@ -200,7 +223,7 @@ def reads_leg(n_gpus):
     names, reads = synth.sample_reads(genome, 25_000_000, np.random.default_rng(4), mean=10000, sd=3000, lo=1000, hi=30000)
     synth.write_fasta(os.path.join(wd, "reads.fasta"), names, reads)
     open(os.path.join(wd, "params.cfg"), "w").write(open(os.path.join(ROOT, "darwin-gpu_b200", "params.cfg")).read())
-    r = subprocess.run([exe, "ref.fasta", "reads.fasta", str(os.cpu_count() or 1)], cwd=wd, capture_output=True, text=True,
+    r = subprocess.run([exe, "ref.fasta", "reads.fasta", str(usable_cores())], cwd=wd, capture_output=True, text=True,
                        env=dict(os.environ, DARWIN_GPUS=str(n_gpus)), timeout=600)
     if r.returncode != 0:
         return {"unavailable": "darwin exited %d: %s" % (r.returncode, r.stderr[-200:])}
