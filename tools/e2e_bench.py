@@ -78,7 +78,7 @@ def main():
         raise SystemExit("darwin failed")
     ours = collect(wd)
     if args.show_stdout:
-        print("\n".join(ln for ln in r.stdout.splitlines() if re.search(r"Time |init|build|driver|num_candidates", ln)), f"\nwall {wall:.3f} s")
+        print("\n".join(ln for ln in r.stdout.splitlines() if re.search(r"Time |init|build|driver|num_candidates|Shard", ln)), f"\nwall {wall:.3f} s")
     summ = json.loads(re.search(r"DARWIN_B200_SUMMARY (\{.*\})", r.stdout).group(1))
     phase = {k: int(v) for k, v in re.findall(r"Time elapsed \(([^)]*)\): (\d+) msec", r.stdout)}
     seeds_ms = [int(x) for x in re.findall(r"Time finding seeds: (\d+) msec", r.stdout)]
