@@ -184,7 +184,7 @@ void GactScheduler::run(const std::vector<GactCall> &calls, std::vector<GactAlig
         return r.i_steps > 0 && r.j_steps > 0;
     };
 
-    // Two groups of candidates ping-pong through the engine's two slots.
+    // Two groups of candidates ping-pong through two of the engine's in-flight slots.
     struct Group {
         std::vector<int32_t> ids;              // active candidates of this group
         std::vector<uint8_t> adv;              // advance flag from the previous tile
