@@ -58,8 +58,9 @@ def config(args, extra=None):
                      "82% full/18% edge, 5.5% first, seed 42 (+rank)",
          "tiles_per_gpu_per_step": args.tiles, "tile_size": TILE, "tile_overlap": OVERLAP,
          "scores": list(SCORES), "parallelism": f"reads/tiles sharded over {args.gpus} GPU(s), no collective",
-         "l2_policy": "inputs larger than L2 are not needed: the tile stream is 0.003 B/cell; each step "
-                      "re-reads descriptors (32 MiB) and rewrites results+states (124 MiB) in HBM"}
+         "l2_policy": "no explicit flush: at the default size one step touches more than the 126 MB L2 (descriptors + "
+                      "tile order 36 MiB, packed bases of 1 Mi tile windows, results + states 128 MiB, direction-window "
+                      "scratch 115 MB), and the kernel is ALU-bound at 0.003 algorithmic bytes per cell"}
     if extra:
         c.update(extra)
     return c
