@@ -18,6 +18,11 @@
  *   cudaSafeCall -> exit(-1)                     int status + gact_last_error()
  *     cuda_header.h:311-319
  *
+ * Optional entry points beyond that boundary (callers and producers either side of the tile path):
+ *   GACT() / GACT_Batch()  gact.cpp:48-228, 231-560        gact_engine_extend()
+ *   SeedPosTable::DSOFT()  seed_pos_table.cpp:100-167      gact_dsoft_create()/_run()
+ *   SeedPosTable()         seed_pos_table.cpp:46-98        gact_seed_table_build()
+ *
  * Plain C types only; no CUDA, C++ or torch types cross this boundary.  All
  * functions return GACT_OK (0) or a negative gact_status; none of them calls
  * exit().  An engine is bound to one device and one stream and is meant to be
