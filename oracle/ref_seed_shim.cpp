@@ -6,7 +6,9 @@
 #include <cstdint>
 #include <cstring>
 #include <vector>
+#define private public          // test-only view of the reference's tables; the class layout is unchanged
 #include "seed_pos_table.h"
+#undef private
 
 extern "C" void *ref_seed_table_new(const char *ref, uint32_t ref_len, int k, uint32_t occ_mult, uint32_t bin_size, uint32_t w)
 {
@@ -25,4 +27,15 @@ extern "C" int ref_dsoft(void *t, const char *q, uint32_t qlen, uint32_t ref_len
     int n = sa->DSOFT((char *)q, qlen, num_seeds, threshold, cand.data(), bins.data(), nz.data(), max_cand);
     for (int i = 0; i < n && i < cap; i++) out[i] = cand[i];
     return n;
+}
+
+// index_table_ (4^k + 1 entries) and pos_table_ (index_table_[4^k] entries) as the reference built them
+extern "C" void ref_seed_table_arrays(void *t, const uint32_t **index, uint64_t *index_entries, const uint32_t **pos,
+                                      uint64_t *n_pos)
+{
+    SeedPosTable *sa = (SeedPosTable *)t;
+    *index = sa->index_table_;
+    *index_entries = sa->index_table_size_;
+    *pos = sa->pos_table_;
+    *n_pos = sa->index_table_[sa->index_table_size_ - 1];
 }

@@ -160,6 +160,30 @@ def make_dsoft_golden():
     print("dsoft golden:", int(sum(counts)), "candidates over", len(counts), "strand calls")
 
 
+def make_seedtable_golden():
+    """SHA-256 of index_table_ / pos_table_ as the reference's own SeedPosTable constructor builds them
+    (seed_pos_table.cpp:46-98) for the inputs of tests/helpers.py:seedtable_cases()."""
+    import ctypes as C
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    R = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libseed_ref.so"))
+    R.ref_seed_table_new.restype = C.c_void_p
+    R.ref_seed_table_new.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
+    R.ref_seed_table_arrays.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+    out = {}
+    for tag, refstr, k, w, b in helpers.seedtable_cases():
+        t = R.ref_seed_table_new(refstr, len(refstr), k, 32, b, w)
+        ip, ie, pp, npos = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
+        R.ref_seed_table_arrays(t, C.byref(ip), C.byref(ie), C.byref(pp), C.byref(npos))
+        index = np.ctypeslib.as_array((C.c_uint32 * ie.value).from_address(ip.value))
+        pos = np.ctypeslib.as_array((C.c_uint32 * max(npos.value, 1)).from_address(pp.value))[:npos.value]
+        out[tag] = helpers.table_digest(index, pos)
+        out[tag].update({"k": k, "w": w, "bin_size": b, "ref_len": len(refstr)})
+        print("seed table golden", tag, out[tag]["n_pos"], "minimizers")
+    json.dump(out, open(os.path.join(HERE, "seedtable_digests.json"), "w"), indent=1)
+
+
 def read_fasta_simple(path):
     recs, name, cur = [], None, []
     for ln in open(path, "rb").read().split(b"\n"):
@@ -180,3 +204,4 @@ if __name__ == "__main__":
     make_e2e_small()
     make_e2e_acgt()
     make_dsoft_golden()
+    make_seedtable_golden()

@@ -6,6 +6,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = os.path.join(HERE, "golden")
+ROOT = os.path.dirname(HERE)
 
 
 def load_kats():
@@ -57,3 +58,36 @@ def compare_batch(res_gpu, st_gpu, res_cpu, st_cpu):
     c[np.arange(P)[None, :] >= res_cpu["n_states"][:, None]] = 0
     bad |= (g != c).any(axis=1)
     return np.nonzero(bad)[0]
+
+
+def seedtable_cases():
+    """Inputs of the seed-position table golden (tests/golden/seedtable_digests.json): (tag, bin-padded reference
+    string, k, w, bin_size).  Deterministic, so the generator (make_golden.py, run where /root/reference exists)
+    and the tests see the same bytes."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "darwin-gpu_b200"))
+    import synth
+    rng = np.random.default_rng(2024)
+    rnd = lambda n: synth.random_genome(n, rng).tobytes()
+
+    def pad(seqs, b):
+        return b"".join(s + b"N" * ((b - len(s) % b) % b) for s in seqs)
+
+    three = [rnd(90000), rnd(40001), rnd(7777)]
+    low = rnd(3000) + b"N" * 9000 + rnd(10) + b"A" * 7000 + rnd(2500) + (b"ACGTTGCA" * 700) + rnd(900).lower() + b"RYKM" * 50
+    return [
+        ("three_k14_w4", pad(three, 64), 14, 4, 64),
+        ("three_k12_w8", pad(three, 64), 12, 8, 64),
+        ("three_k11_w10_b128", pad(three, 128), 11, 10, 128),
+        ("lowcomplexity_k10_w4", pad([low], 64), 10, 4, 64),
+        ("lowcomplexity_k8_w1", pad([low], 64), 8, 1, 64),
+        ("polyA_k9_w3", b"A" * 20000, 9, 3, 64),
+        ("blockedge_k9_w3", pad([rnd(2048 + 3 - 1) + b"C" * 5000 + rnd(100)], 64), 9, 3, 64),
+    ]
+
+
+def table_digest(index, pos):
+    import hashlib
+    return {"index_entries": int(len(index)), "n_pos": int(len(pos)),
+            "index_sha256": hashlib.sha256(np.ascontiguousarray(index, dtype=np.uint32).tobytes()).hexdigest(),
+            "pos_sha256": hashlib.sha256(np.ascontiguousarray(pos, dtype=np.uint32).tobytes()).hexdigest()}

@@ -111,6 +111,46 @@ def test_dsoft_matches_reference_golden(host):
     assert (np.concatenate(got) == z["cands"]).all()
 
 
+def test_seed_table_matches_reference_golden(host):
+    """index_table_ / pos_table_ of the host builder equal the reference's own SeedPosTable constructor
+    (seed_pos_table.cpp:46-98): SHA-256 digests committed by tests/golden/make_golden.py, and -- where the reference
+    was built in place (oracle/_ref) -- the live tables word for word."""
+    import json
+    from helpers import seedtable_cases, table_digest
+    host.dh_seed_table_arrays.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+    gold = json.load(open(os.path.join(GOLD, "seedtable_digests.json")))
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libseed_ref.so")
+    R = None
+    if os.path.exists(ref_so):
+        R = C.CDLL(ref_so)
+        if hasattr(R, "ref_seed_table_arrays"):
+            R.ref_seed_table_new.restype = C.c_void_p
+            R.ref_seed_table_new.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
+            R.ref_seed_table_arrays.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        else:
+            R = None
+    cases = seedtable_cases()
+    assert sorted(gold) == sorted(c[0] for c in cases)
+    for tag, refstr, k, w, b in cases:
+        t = host.dh_seed_table_new(refstr, len(refstr), k, 32, b, w, 4)
+        assert t
+        ip, ie, pp, npos, mo = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64(), C.c_uint32()
+        host.dh_seed_table_arrays(t, C.byref(ip), C.byref(ie), C.byref(pp), C.byref(npos), C.byref(mo))
+        index = np.ctypeslib.as_array((C.c_uint32 * ie.value).from_address(ip.value))
+        pos = np.ctypeslib.as_array((C.c_uint32 * max(npos.value, 1)).from_address(pp.value))[:npos.value]
+        d = table_digest(index, pos)
+        for key in ("index_entries", "n_pos", "index_sha256", "pos_sha256"):
+            assert d[key] == gold[tag][key], (tag, key)
+        if R is not None:
+            rt = R.ref_seed_table_new(refstr, len(refstr), k, 32, b, w)
+            rip, rie, rpp, rn = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
+            R.ref_seed_table_arrays(rt, C.byref(rip), C.byref(rie), C.byref(rpp), C.byref(rn))
+            assert rie.value == ie.value and rn.value == npos.value
+            assert np.array_equal(np.ctypeslib.as_array((C.c_uint32 * rie.value).from_address(rip.value)), index)
+            assert np.array_equal(np.ctypeslib.as_array((C.c_uint32 * max(rn.value, 1)).from_address(rpp.value))[:rn.value], pos)
+        host.dh_seed_table_free(t)
+
+
 def test_cli_usage_and_no_gpu_behaviour(tmp_path):
     """The drop-in binary keeps the reference's usage line; without a GPU it refuses to run
     (no CPU fallback on the GACT path)."""

@@ -60,6 +60,25 @@ def test_seed_table_matches_host_builder(pygact):
         check(G, H, eng, pad(genome), 8, 1)           # w = 1: every position is its own minimizer
 
 
+def test_seed_table_matches_reference_golden(pygact):
+    """Tables built on the device against the digests of the reference's own SeedPosTable constructor
+    (tests/golden/seedtable_digests.json, written by make_golden.py where /root/reference exists)."""
+    import json
+    from helpers import seedtable_cases, table_digest
+    G = pygact
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "seedtable_digests.json")))
+    with G.GactEngine(max_tiles=16) as eng:
+        for tag, refstr, k, w, b in seedtable_cases():
+            tab = G.SeedTable(eng, refstr, kmer_size=k, seed_occurence_multiple=32, bin_size=b, window_size=w)
+            try:
+                index, pos = tab.download()
+            finally:
+                tab.close()
+            d = table_digest(index, pos)
+            for key in ("index_entries", "n_pos", "index_sha256", "pos_sha256"):
+                assert d[key] == gold[tag][key], (tag, key)
+
+
 def test_seed_table_low_complexity_and_block_edges(pygact):
     """Constant-minimum runs (poly-A, N padding, tandem repeats) longer than a thread block's 2048 positions carry
     their run start across blocks; lower-case and non-ACGT bytes follow ntcoding.cpp:60-72."""
