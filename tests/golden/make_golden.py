@@ -184,6 +184,27 @@ def make_seedtable_golden():
     json.dump(out, open(os.path.join(HERE, "seedtable_digests.json"), "w"), indent=1)
 
 
+def make_tiny_golden():
+    """Queues of the reference's own AlignWithBT (align.cpp:60-233) for every 7th tile of the exhaustive tiny-tile
+    batch (tests/helpers.py:tiny_tile_batch), three scoring schemes, early_terminate 2 and 8."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    mb = helpers.tiny_tile_batch()
+    sub = helpers.tiny_golden_subset(len(mb["ref_off"]))
+    flat, offs = [], [0]
+    for scores in helpers.TINY_SCHEMES:
+        for T, ov in helpers.TINY_ENGINES:
+            for t in sub:
+                r = mb["ref"][mb["ref_off"][t]:mb["ref_off"][t] + mb["ref_len"][t]].tobytes()
+                q = mb["query"][mb["query_off"][t]:mb["query_off"][t] + mb["query_len"][t]].tobytes()
+                queue = O.ref_align_tile(r, q, scores, int(mb["reverse"][t]), int(mb["first"][t]), T - ov)
+                flat += queue
+                offs.append(len(flat))
+    np.savez_compressed(os.path.join(HERE, "tiny_tiles.npz"), flat=np.asarray(flat, dtype=np.int16),
+                        offs=np.asarray(offs, dtype=np.int32))
+    print("tiny golden:", len(offs) - 1, "reference queues")
+
+
 def read_fasta_simple(path):
     recs, name, cur = [], None, []
     for ln in open(path, "rb").read().split(b"\n"):
@@ -205,3 +226,4 @@ if __name__ == "__main__":
     make_e2e_acgt()
     make_dsoft_golden()
     make_seedtable_golden()
+    make_tiny_golden()

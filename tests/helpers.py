@@ -91,3 +91,33 @@ def table_digest(index, pos):
     return {"index_entries": int(len(index)), "n_pos": int(len(pos)),
             "index_sha256": hashlib.sha256(np.ascontiguousarray(index, dtype=np.uint32).tobytes()).hexdigest(),
             "pos_sha256": hashlib.sha256(np.ascontiguousarray(pos, dtype=np.uint32).tobytes()).hexdigest()}
+
+
+TINY_SCHEMES = [(1, -1, -1, -1), (2, -3, -5, -2), (1, -1, -2, -1)]
+TINY_ENGINES = [(8, 6), (8, 0)]          # (tile_size, tile_overlap): early_terminate 2 and 8 (>= every length below)
+
+
+def tiny_tile_batch():
+    """Every pair of strings over {A,C,G} of length 1..3, both directions, first and non-first: 6 084 tiles whose DP
+    is small enough that all tie situations of align.cpp:138-177 occur (M = I = D, all-non-positive cells, equal
+    open/extend, several equal maxima).  Returns a tile batch dict like synth.tile_microbatch()."""
+    import itertools
+    strings = [("".join(p)).encode() for n in (1, 2, 3) for p in itertools.product("ACG", repeat=n)]
+    ref, query, ro, qo, rl, ql, rev, first = [], [], [], [], [], [], [], []
+    rpos = qpos = 0
+    for r in strings:
+        for q in strings:
+            for rv in (0, 1):
+                for f in (0, 1):
+                    ref.append(r); query.append(q)
+                    ro.append(rpos); qo.append(qpos); rl.append(len(r)); ql.append(len(q)); rev.append(rv); first.append(f)
+                    rpos += len(r); qpos += len(q)
+    return dict(ref=np.frombuffer(b"".join(ref), dtype=np.uint8).copy(), query=np.frombuffer(b"".join(query), dtype=np.uint8).copy(),
+                ref_off=np.asarray(ro, dtype=np.int64), query_off=np.asarray(qo, dtype=np.int64),
+                ref_len=np.asarray(rl, dtype=np.int32), query_len=np.asarray(ql, dtype=np.int32),
+                reverse=np.asarray(rev, dtype=np.uint8), first=np.asarray(first, dtype=np.uint8))
+
+
+def tiny_golden_subset(n):
+    """Indices of the tiles whose reference outputs are committed (every 7th tile)."""
+    return np.arange(0, n, 7)
