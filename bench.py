@@ -403,6 +403,7 @@ def main():
                 "note": "frac can exceed 1: the tagged-max formulation executes ~6 ALU-pipe instructions per cell instead "
                         "of the 17 (8.5 packed) the roofline model assumes; ncu of the same kernel: ALU pipe 86 % busy, issue slots 67 % "
                         "(profiles/r1_s16h_tile_kernel_ncu.txt)",
+                "alu_pipe_busy_ncu": 0.8607 if (packed and TILE == 320) else None,   # sm__inst_executed_pipe_alu, profiles/r1_s16h_tile_kernel_ncu.txt
                 "peak_alu_fma_mix": peak_mix, "peak_source": "gact_int_peak (own microbenchmark, measured in this run)",
                 "kernel_ms": kernel_ms,
                 "hbm": {"achieved": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
