@@ -1135,8 +1135,42 @@ int gact_engine_extend(gact_engine *e, int n, const gact_call *calls, gact_align
     // measured faster (profiles/r1_chain_order.txt)
     int deal = (!latency_mode && n <= e->s16h.ctas * e->s16h.warps_per_cta * e->s16h.tpw()) ? 1 : 0;
     if (getenv("GACT_CHAIN_DEAL")) deal = atoi(getenv("GACT_CHAIN_DEAL"));
-    s16h_launch_chain(latency_mode ? e->s16h_lat : e->s16h, e->kp, e->d_chain_calls, n, e->d_chain_res, e->params.first_tile_score_threshold,
-                      s.d_counters + 1, st, deal);
+    // More chains than slots: a tile of a resident chain takes ~160 us at full occupancy, so the longest reads
+    // (150 tiles for 30 kb) would outlast the rest of the shard.  The chains whose serial length exceeds 60 % of
+    // the average load per chain slot go to the one-tile-per-warp kernel, launched first on its own stream with
+    // at most one CTA per SM; the two-tiles-per-warp kernel takes the remaining calls and the remaining SM space.
+    int n_long = 0;
+    if (!latency_mode && e->s16h_lat.ok && !(getenv("GACT_CHAIN_LONG") && atoi(getenv("GACT_CHAIN_LONG")) == 0)) {
+        const int et = std::max(1, e->params.tile_size - e->params.tile_overlap);
+        const double slots = (double)e->s16h.ctas * e->s16h.warps_per_cta * e->s16h.tpw();
+        double total = 0.0;
+        for (int i = 0; i < n; i++) total += (double)(cc[(size_t)i].query_len / et + 2);
+        const double long_tiles = 0.6 * total / slots;
+        const int cap_long = e->num_sms * e->s16h_lat.warps_per_cta;
+        while (n_long < n && n_long < cap_long && (double)(cc[(size_t)n_long].query_len / et + 2) > long_tiles) n_long++;
+        if (n_long < 8) n_long = 0;
+    }
+    if (n_long > 0) {
+        Slot &s1 = e->slots[1];
+        CU(e, cudaEventRecord(s1.ev_fork, st));
+        CU(e, cudaStreamWaitEvent(e->cs[1], s1.ev_fork, 0));
+        s16h_launch_chain(e->s16h_lat, e->kp, e->d_chain_calls, n_long, e->d_chain_res, e->params.first_tile_score_threshold,
+                          s.d_counters + 0, e->cs[1], 0);
+        CU(e, cudaGetLastError());
+        CU(e, cudaEventRecord(s1.ev_k1, e->cs[1]));
+        const int n_rest = n - n_long;
+        if (n_rest > 0) {
+            int deal_rest = (n_rest <= e->s16h.ctas * e->s16h.warps_per_cta * e->s16h.tpw()) ? 1 : 0;
+            if (getenv("GACT_CHAIN_DEAL")) deal_rest = atoi(getenv("GACT_CHAIN_DEAL"));
+            s16h_launch_chain(e->s16h, e->kp, e->d_chain_calls + n_long, n_rest, e->d_chain_res + n_long,
+                              e->params.first_tile_score_threshold, s.d_counters + 1, st, deal_rest);
+        }
+        CU(e, cudaStreamWaitEvent(st, s1.ev_k1, 0));
+        e->stats.kernel_launches++;
+    } else {
+        s16h_launch_chain(latency_mode ? e->s16h_lat : e->s16h, e->kp, e->d_chain_calls, n, e->d_chain_res, e->params.first_tile_score_threshold,
+                          s.d_counters + 1, st, deal);
+    }
     CU(e, cudaGetLastError());
     CU(e, cudaEventRecord(e->ev_c1, st));
     std::vector<ChainResult> res((size_t)n);
