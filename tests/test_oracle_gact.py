@@ -2,7 +2,6 @@
 build.  Candidates come from the host D-SOFT (pinned to the reference by tests/test_host.py), are converted as in
 darwin.cpp:215-224 / 254-263, extended by the oracle, formatted as in gact.cpp:214-224, and the sorted|uniq lines
 must equal the golden output of the unmodified reference (`darwin_ref`, tests/golden/e2e_*/expected_*.txt)."""
-import ctypes as C
 import os
 
 import numpy as np

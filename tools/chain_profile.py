@@ -3,7 +3,6 @@
 import ctypes as C
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "darwin-gpu_b200"))

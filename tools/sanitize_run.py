@@ -5,7 +5,6 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "darwin-gpu_b200"))
-import numpy as np
 import pygact as G
 import synth
 
