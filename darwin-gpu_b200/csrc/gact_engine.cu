@@ -69,8 +69,7 @@ struct gact_engine {
     int warps_per_cta = 0, ctas = 0;
     size_t smem_main = 0;
     uint8_t *d_gscratch = nullptr;
-    S16Plan s16;              // packed s16x2 kernel launch plan (s16.ok: usable for these params)
-    S16HPlan s16h;            // two-tiles-per-warp mapping of the same kernel (tile_size <= 320)
+    S16HPlan s16h;            // packed s16x2 kernels: two tiles per warp (tile_size <= 320) or one (<= 1024); ok = usable for these params
     S16HPlan s16h_lat;        // chain kernel, one tile per warp: used when candidates < chain slots (latency bound)
     SeqSetHost sets[GACT_MAX_SETS];
     Slot slots[GACT_MAX_INFLIGHT];
@@ -243,26 +242,19 @@ int plan_launch(gact_engine *e)
     CU(e, cudaFuncSetAttribute((const void *)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_main));
     first_fn ff = pick_first_i32(C);
     CU(e, cudaFuncSetAttribute((const void *)ff, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * TS));
-    // experiment knobs (not part of the ABI): GACT_S16_WINDOW=smem|global, GACT_S16_WARPS=<per SM>
-    int mode = 0, wps = 0;
-    if (const char *m = getenv("GACT_S16_WINDOW")) mode = (strcmp(m, "global") == 0) ? 2 : (strcmp(m, "smem") == 0) ? 1 : 0;
+    // experiment knob (not part of the ABI): GACT_S16_WARPS=<resident warps per SM>
+    int wps = 0;
     if (const char *w = getenv("GACT_S16_WARPS")) wps = atoi(w);
-    // GACT_S16_HALF=0 disables the two-tiles-per-warp mapping
-    const char *hv = getenv("GACT_S16_HALF");
-    if (!(hv && atoi(hv) == 0) && mode != 1) {
-        if (s16h_make_plan(e->params, e->num_sms, wps, &e->s16h) != 0 ||
-            s16h_make_plan(e->params, e->num_sms, wps, &e->s16h_lat, true) != 0)
-            return fail(e, GACT_ERR_CUDA, "s16h kernel attribute setup failed");
-    }
-    return s16_make_plan(e->params, e->num_sms, mode, wps, &e->s16) == 0
-               ? GACT_OK
-               : fail(e, GACT_ERR_CUDA, "s16 kernel attribute setup failed");
+    if (s16h_make_plan(e->params, e->num_sms, wps, &e->s16h) != 0 ||
+        s16h_make_plan(e->params, e->num_sms, wps, &e->s16h_lat, true) != 0)
+        return fail(e, GACT_ERR_CUDA, "s16h kernel attribute setup failed");
+    return GACT_OK;
 }
 
 bool use_s16(const gact_engine *e)
 {
     if (e->variant_req == 1) return false;
-    return e->s16.ok;
+    return e->s16h.ok;
 }
 
 int launch_batch(gact_engine *e, Slot &s, cudaStream_t st, int scratch_region)
@@ -271,7 +263,7 @@ int launch_batch(gact_engine *e, Slot &s, cudaStream_t st, int scratch_region)
     CU(e, cudaMemsetAsync(s.d_counters, 0, 2 * sizeof(int), st));
     CU(e, cudaEventRecord(s.ev_k0, st));
     const int TS = e->C * 32;
-    if (s.n_first > 0 && use_s16(e) && e->s16h.ok) {
+    if (s.n_first > 0 && use_s16(e)) {
         s16h_launch_first(e->s16h, e->kp, s.d_descs, s.d_first, s.n_first, s.d_eff, s.d_counters + 0, st);
         e->stats.kernel_launches++;
     } else if (s.n_first > 0) {
@@ -282,12 +274,9 @@ int launch_batch(gact_engine *e, Slot &s, cudaStream_t st, int scratch_region)
         ff<<<ctas, 256, 8 * TS, st>>>(e->kp, s.d_descs, s.d_first, s.n_first, s.d_eff, s.d_counters + 0);
         e->stats.kernel_launches++;
     }
-    if (use_s16(e) && e->s16h.ok) {
+    if (use_s16(e)) {
         s16h_launch(e->s16h, e->kp, s.d_descs, s.d_order, s.n, s.d_eff, s.d_results, s.d_states, e->pitch_words,
                     s.d_counters + 1, st, scratch_region);
-    } else if (use_s16(e)) {
-        s16_launch(e->s16, e->kp, s.d_descs, s.n, s.d_eff, s.d_results, s.d_states, e->pitch_words,
-                   s.d_counters + 1, st);
     } else {
         main_fn f = pick_main_i32(e->C, e->dir_global);
         int ctas = e->ctas;
@@ -504,7 +493,6 @@ void gact_engine_destroy(gact_engine *e)
     for (int i = 0; i < GACT_MAX_SETS; i++) free_set(e->sets[i]);
     for (int k = 0; k < GACT_MAX_INFLIGHT; k++) free_slot(e->slots[k]);
     if (e->d_gscratch) cudaFree(e->d_gscratch);
-    s16_free_plan(&e->s16);
     s16h_free_plan(&e->s16h);
     s16h_free_plan(&e->s16h_lat);
     if (e->d_chain_calls) cudaFree(e->d_chain_calls);
@@ -529,16 +517,17 @@ int gact_engine_upload(gact_engine *e, int set, int64_t n_seqs, const char *cons
     SeqSetHost &s = e->sets[set];
     free_set(s);
     e->kp.sets[set] = SeqSetDev{nullptr, nullptr, 0};
+    // the set becomes visible (len, starts, device pointers) only once every step below has succeeded: a failed
+    // upload leaves it empty, so descriptor validation rejects tiles that would address it
     long long total = 0;
-    s.starts.resize((size_t)n_seqs + 1);
+    std::vector<long long> starts((size_t)n_seqs + 1);
     for (int64_t i = 0; i < n_seqs; i++) {
         if (lens[i] < 0 || (lens[i] > 0 && !seqs[i])) return fail(e, GACT_ERR_ARG, "bad sequence in upload");
-        s.starts[(size_t)i] = total;
+        starts[(size_t)i] = total;
         total += lens[i];
     }
-    s.starts[(size_t)n_seqs] = total;
-    s.len = total;
-    if (total == 0) { s.bits = 0; return GACT_OK; }
+    starts[(size_t)n_seqs] = total;
+    if (total == 0) { s.starts = starts; s.len = 0; s.bits = 0; return GACT_OK; }
 
     // stage through pinned memory in chunks, concatenating on the device
     uint8_t *d_raw = nullptr;
@@ -591,6 +580,8 @@ int gact_engine_upload(gact_engine *e, int set, int64_t n_seqs, const char *cons
     if (r != cudaSuccess) { cudaFree(d_raw); cudaFree(d_packed); return fail(e, GACT_ERR_CUDA, std::string("pack kernel: ") + cudaGetErrorString(r)); }
     if (h_flag) { cudaFree(d_packed); s.d_bytes = d_raw; s.bits = 8; }
     else        { cudaFree(d_raw); s.d_packed = d_packed; s.bits = 2; }
+    s.starts.swap(starts);
+    s.len = total;
     e->kp.sets[set] = SeqSetDev{s.d_packed, s.d_bytes, s.len};
     return GACT_OK;
 }
@@ -625,7 +616,7 @@ int gact_engine_submit(gact_engine *e, int n, const gact_tile_desc *descs)
     // The two slots launch on their own streams, ordered after the work already enqueued on the
     // caller's stream.  Kernels that share one scratch area (int32 / one-tile-per-warp variants) stay
     // on one stream.
-    const bool overlap = use_s16(e) && e->s16h.ok;
+    const bool overlap = use_s16(e);
     cudaStream_t st = e->cs[overlap ? e->head : 0];
     CU(e, cudaEventRecord(s.ev_fork, e->stream));
     CU(e, cudaStreamWaitEvent(st, s.ev_fork, 0));
@@ -782,7 +773,7 @@ int gact_engine_set_kernel(gact_engine *e, int variant)
 {
     if (!e) return GACT_ERR_ARG;
     if (variant < 0 || variant > 2) return fail(e, GACT_ERR_ARG, "unknown kernel variant");
-    if (variant == 2 && !e->s16.ok) return fail(e, GACT_ERR_ARG, "s16x2 kernel cannot run these parameters");
+    if (variant == 2 && !e->s16h.ok) return fail(e, GACT_ERR_ARG, "s16x2 kernel cannot run these parameters");
     e->variant_req = variant;
     return GACT_OK;
 }
@@ -1081,7 +1072,7 @@ int gact_engine_extend(gact_engine *e, int n, const gact_call *calls, gact_align
 {
     if (!e || n < 0 || (n > 0 && (!calls || !out))) return GACT_ERR_ARG;
     if (!gact_engine_extend_supported(e))
-        return fail(e, GACT_ERR_ARG, "on-device extension needs tile_size <= 320, 16-bit score range and ACGT-only sets");
+        return fail(e, GACT_ERR_ARG, "on-device extension needs scores in the packed kernels' 16-bit range and ACGT-only sets");
     if (e->inflight || e->staged) return fail(e, GACT_ERR_STATE, "extend while batches are outstanding");
     if (n == 0) return GACT_OK;
     CU(e, cudaSetDevice(e->device));
@@ -1196,3 +1187,14 @@ int gact_engine_extend(gact_engine *e, int n, const gact_call *calls, gact_align
 }
 
 }  // extern "C"
+
+#ifdef GACT_PROF
+// profiling build only (libgact_b200_prof.so): read and clear the chain kernel's phase clocks
+extern "C" int gact_prof_read(unsigned long long *out8)
+{
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out8, gact::g_chain_prof, sizeof(z)) != cudaSuccess) return GACT_ERR_CUDA;
+    if (cudaMemcpyToSymbol(gact::g_chain_prof, z, sizeof(z)) != cudaSuccess) return GACT_ERR_CUDA;
+    return GACT_OK;
+}
+#endif

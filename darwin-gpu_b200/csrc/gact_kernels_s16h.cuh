@@ -560,6 +560,20 @@ struct ChainResult {
     long long n_cells;
 };
 
+#ifdef GACT_PROF
+// per-phase clock accounting of the chain kernel (tools/chain_latency.py, libgact_b200_prof.so only)
+__device__ unsigned long long g_chain_prof[8];
+#define PROF_DECL long long prof_t0 = clock64(); unsigned long long prof_acc[7] = {0, 0, 0, 0, 0, 0, 0}
+#define PROF_MARK(slot) do { const long long prof_t1 = clock64(); prof_acc[slot] += (unsigned long long)(prof_t1 - prof_t0); prof_t0 = prof_t1; } while (0)
+#define PROF_COUNT(slot, v) prof_acc[slot] += (unsigned long long)(v)
+#define PROF_FLUSH(cond) do { if (cond) { for (int x = 0; x < 7; x++) if (prof_acc[x]) atomicAdd(&g_chain_prof[x], prof_acc[x]); } } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(slot)
+#define PROF_COUNT(slot, v)
+#define PROF_FLUSH(cond)
+#endif
+
 template <int CS, int LANES>
 __global__ void __launch_bounds__(128, (CS <= 10 ? 3 : 2))
 gact_chain_s16h_kernel(const __grid_constant__ KParams P, const ChainCall *__restrict__ calls, int n_calls,
@@ -587,6 +601,7 @@ gact_chain_s16h_kernel(const __grid_constant__ KParams P, const ChainCall *__res
     constexpr int SEGS = 32 / LANES;
     const int lseg = (threadIdx.x >> 5) * SEGS + cx.segbase / LANES;
     const int n_first = deal ? (int)gridDim.x * (int)(blockDim.x >> 5) * SEGS : 0;   // calls dealt by the fixed first claims
+    PROF_DECL;
 
     for (;;) {
         // ---- next tile of this segment's candidate (loop heads of gact.cpp:82 and :144) ----
@@ -649,6 +664,7 @@ gact_chain_s16h_kernel(const __grid_constant__ KParams P, const ChainCall *__res
             }
         }
         if (!__any_sync(FULL, have)) break;
+        PROF_MARK(0);
 
         // ---- the tile: stage, (first pass), DP, traceback ----
         int n = have ? t_rl : 0, m = have ? t_ql : 0;
@@ -656,6 +672,7 @@ gact_chain_s16h_kernel(const __grid_constant__ KParams P, const ChainCall *__res
         seg_stage<CS, LANES, true>(cx, rset, qset, roff, t_rl, qoff, t_ql, reverse, n, m);
         uint32_t q[CS];
         seg_load_q<CS, LANES, true>(cx, m, q);
+        PROF_MARK(1);
         const bool is_first = have && first_tile;
         int mi = n, mj = m;
         if (__any_sync(FULL, is_first)) {
@@ -663,10 +680,14 @@ gact_chain_s16h_kernel(const __grid_constant__ KParams P, const ChainCall *__res
             seg_first_pass<CS, LANES, true>(cx, q, is_first ? n : 0, is_first ? m : 0, &fi, &fj);
             if (is_first) { mi = fi; mj = fj; n = fi; m = fj; }           // sub-tile ending at the last maximum
         }
+        PROF_MARK(2);
         DirWinH<CS> dw;
         dw.init(cx.dirbase, n, m, P);
         const int tile_score = seg_dp<CS, LANES, true>(cx, q, n, m, dw);
+        PROF_MARK(3);
         const SegTrace tr = seg_traceback<CS, LANES, false>(cx, dw, n, m, tile_score, nullptr, prev_gap);
+        PROF_MARK(4);
+        PROF_COUNT(6, 1);
 
         // ---- consume (bodies of the loops at gact.cpp:95-133 and :158-194) ----
         if (have) {
@@ -697,7 +718,9 @@ gact_chain_s16h_kernel(const __grid_constant__ KParams P, const ChainCall *__res
             }
         }
         __syncwarp();
+        PROF_MARK(5);
     }
+    PROF_FLUSH(cx.lane == 0);
 }
 
 // ---------------------------------------------------------------------------

@@ -49,8 +49,13 @@ int *Align_Batch_GPU(std::vector<std::string> ref_seqs, std::vector<std::string>
         rp.push_back(ref_seqs[t].data()); rl.push_back(ref_lens[t]);
         qp.push_back(query_seqs[t].data()); ql.push_back(query_lens[t]); slot.push_back(t);
     }
-    gact_engine_upload(e, GACT_SET_REF, rp.size(), rp.data(), rl.data());     // bytes 0..3 -> 8-bit set
-    gact_engine_upload(e, GACT_SET_AUX, qp.size(), qp.data(), ql.data());
+    // bytes 0..3 -> 8-bit sets.  sub_mat is not consulted: the reference's own Align_Batch_GPU receives it and
+    // never reads it either (cuda_host.cu:26 is its only mention; the kernel scores with the match/mismatch
+    // constants of GPU_init), so base 4 ('N') against base 4 scores as a match on both sides.
+    if (gact_engine_upload(e, GACT_SET_REF, rp.size(), rp.data(), rl.data()) != GACT_OK ||
+        gact_engine_upload(e, GACT_SET_AUX, qp.size(), qp.data(), ql.data()) != GACT_OK) {
+        fprintf(stderr, "%s\n", gact_last_error(e)); exit(-1);                 // the reference exits on CUDA errors
+    }
     std::vector<gact_tile_desc> d(slot.size());
     for (size_t k = 0; k < slot.size(); ++k) {
         const int t = slot[k];

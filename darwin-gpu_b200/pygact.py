@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgact_b200.so")
+LIB_PATH = os.environ.get("GACT_LIB") or os.path.join(HERE, "libgact_b200.so")     # GACT_LIB: profiling builds (tools/)
 
 GACT_OK = 0
 SET_REF, SET_READS, SET_READS_RC, SET_AUX = 0, 1, 2, 3

@@ -211,8 +211,8 @@ int gact_engine_get_kernel(const gact_engine *e);
 /* ---- whole candidate extensions on the device (GACT(), gact.cpp:48-228) ----
  * One call = one D-SOFT candidate: left extension, right extension from the first tile's maximum,
  * first-tile threshold, total score -- the tile chain is walked on the GPU, the host gets one
- * gact_alignment per call and no traceback states.  Supported when the packed two-tiles-per-warp kernel
- * can run the engine's parameters (tile_size <= 320, scores in the 16-bit range) and the sets in use
+ * gact_alignment per call and no traceback states.  Supported when the packed s16x2 kernels can run the
+ * engine's parameters (any tile_size <= GACT_MAX_TILE_SIZE with scores in the 16-bit range) and the sets in use
  * hold only ACGT; otherwise GACT_ERR_ARG is returned and the caller drives tiles itself
  * (gact_engine_submit/wait, as host/gact_scheduler.cpp does). */
 typedef struct {

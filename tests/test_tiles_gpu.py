@@ -11,12 +11,15 @@ pytestmark = pytest.mark.gpu
 VARIANTS = [1, 2]        # 1 = int32 DPX kernel, 2 = packed s16x2 DPX kernel
 
 
-def _engine(G, variant, **kw):
+def _engine(G, variant, soft=False, **kw):
+    """soft: return None instead of skipping the whole test when the variant cannot run these parameters."""
     eng = G.GactEngine(**kw)
     try:
         eng.set_kernel(variant)
     except G.GactError:
         eng.close()
+        if soft:
+            return None
         pytest.skip(f"kernel variant {variant} not available for these parameters")
     return eng
 
@@ -41,14 +44,20 @@ def test_golden_random_tiles(pygact, variant):
     groups = {}
     for v in vecs:
         groups.setdefault((v["scores"], v["et"]), []).append(v)
+    ran = 0
     for (sc, et), vs in groups.items():
         T = max(320, et + 1)
-        with _engine(G, variant, match=sc[0], mismatch=sc[1], gap_open=sc[2], gap_extend=sc[3],
-                     tile_size=T, tile_overlap=T - et, max_tiles=256) as eng:
+        eng = _engine(G, variant, soft=True, match=sc[0], mismatch=sc[1], gap_open=sc[2], gap_extend=sc[3],
+                      tile_size=T, tile_overlap=T - et, max_tiles=256)
+        if eng is None:
+            continue        # outside the packed kernel's 16-bit score range: only this group is left to the int32 kernel
+        with eng:
             out = G.align_batch(eng, [v["ref"] for v in vs], [v["query"] for v in vs],
                                 [v["reverse"] for v in vs], [v["first"] for v in vs])
         for v, q in zip(vs, out):
             assert q == v["queue"], (sc, et, len(v["ref"]), len(v["query"]), v["reverse"], v["first"])
+        ran += len(vs)
+    assert ran >= (len(vecs) if variant == 1 else 340), f"only {ran} of {len(vecs)} golden tiles ran on variant {variant}"
 
 
 def _run_microbatch(G, O, variant, n, seed, tile=320, overlap=120, scores=(1, -1, -1, -1), **mbkw):
