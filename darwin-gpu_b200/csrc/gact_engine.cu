@@ -50,6 +50,9 @@ struct Slot {
 
 }  // namespace
 
+struct gact_chain_state;
+static void destroy_chain_state(struct gact_engine *e);
+
 struct gact_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -76,10 +79,7 @@ struct gact_engine {
     int head = 0, tail = 0, inflight = 0;   // async ring
     bool staged = false;
     double last_kernel_ms = -1.0;
-    ChainCall *d_chain_calls = nullptr;      // gact_engine_extend buffers (grown on demand)
-    ChainResult *d_chain_res = nullptr;
-    size_t chain_cap = 0;
-    cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;
+    struct gact_chain_state *chains = nullptr;       // gact_engine_extend_* state (created on first use)
     gact_stats stats{};
     std::string err;
 };
@@ -495,10 +495,7 @@ void gact_engine_destroy(gact_engine *e)
     if (e->d_gscratch) cudaFree(e->d_gscratch);
     s16h_free_plan(&e->s16h);
     s16h_free_plan(&e->s16h_lat);
-    if (e->d_chain_calls) cudaFree(e->d_chain_calls);
-    if (e->d_chain_res) cudaFree(e->d_chain_res);
-    if (e->ev_c0) cudaEventDestroy(e->ev_c0);
-    if (e->ev_c1) cudaEventDestroy(e->ev_c1);
+    destroy_chain_state(e);
     if (e->s_h2d) { cudaStreamSynchronize(e->s_h2d); cudaStreamDestroy(e->s_h2d); }
     if (e->s_d2h) { cudaStreamSynchronize(e->s_d2h); cudaStreamDestroy(e->s_d2h); }
     for (int k = 0; k < GACT_MAX_INFLIGHT; k++) if (e->cs[k]) { cudaStreamSynchronize(e->cs[k]); cudaStreamDestroy(e->cs[k]); }
@@ -1040,6 +1037,84 @@ double gact_dsoft_last_kernel_ms(const gact_dsoft *d) { return d ? d->last_ms : 
 
 // ===========================================================================
 // whole candidate extensions on the device
+namespace {
+
+// resources of one extend batch in flight
+struct ChainBatch {
+    ChainCall *d_calls = nullptr, *h_calls = nullptr;       // device / pinned host
+    ChainResult *d_res = nullptr, *h_res = nullptr;
+    ChainAux *d_aux = nullptr;                              // [2]: main launch, long-chain lane
+    int *d_taken = nullptr;
+    size_t cap = 0;
+    std::vector<int> perm;                                  // device order -> caller's order
+    int n = 0;
+    bool busy = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_lane = nullptr, ev_done = nullptr;
+};
+
+void free_chain_batch(ChainBatch &b)
+{
+    if (b.d_calls) cudaFree(b.d_calls);
+    if (b.d_res) cudaFree(b.d_res);
+    if (b.d_aux) cudaFree(b.d_aux);
+    if (b.d_taken) cudaFree(b.d_taken);
+    if (b.h_calls) cudaFreeHost(b.h_calls);
+    if (b.h_res) cudaFreeHost(b.h_res);
+    for (cudaEvent_t ev : {b.ev0, b.ev1, b.ev_fork, b.ev_lane, b.ev_done}) if (ev) cudaEventDestroy(ev);
+    b = ChainBatch();
+}
+
+int reserve_chain_batch(gact_engine *e, ChainBatch &b, size_t n)
+{
+    if (!b.ev0) {
+        CU(e, cudaEventCreate(&b.ev0));
+        CU(e, cudaEventCreate(&b.ev1));
+        CU(e, cudaEventCreateWithFlags(&b.ev_fork, cudaEventDisableTiming));
+        CU(e, cudaEventCreateWithFlags(&b.ev_lane, cudaEventDisableTiming));
+        CU(e, cudaEventCreateWithFlags(&b.ev_done, cudaEventDisableTiming));
+    }
+    if (n <= b.cap) return GACT_OK;
+    if (b.d_calls) cudaFree(b.d_calls);
+    if (b.d_res) cudaFree(b.d_res);
+    if (b.d_taken) cudaFree(b.d_taken);
+    if (b.h_calls) cudaFreeHost(b.h_calls);
+    if (b.h_res) cudaFreeHost(b.h_res);
+    b.d_calls = nullptr; b.d_res = nullptr; b.d_taken = nullptr; b.h_calls = nullptr; b.h_res = nullptr; b.cap = 0;
+    const size_t want = std::max<size_t>(n, 256);
+    if ((!b.d_aux && cudaMalloc(&b.d_aux, 2 * sizeof(ChainAux)) != cudaSuccess) ||
+        cudaMalloc(&b.d_calls, want * sizeof(ChainCall)) != cudaSuccess ||
+        cudaMalloc(&b.d_res, want * sizeof(ChainResult)) != cudaSuccess ||
+        cudaMalloc(&b.d_taken, want * sizeof(int)) != cudaSuccess ||
+        cudaMallocHost(&b.h_calls, want * sizeof(ChainCall)) != cudaSuccess ||
+        cudaMallocHost(&b.h_res, want * sizeof(ChainResult)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(e, GACT_ERR_NOMEM, "allocation of the chain buffers failed");
+    }
+    b.cap = want;
+    return GACT_OK;
+}
+
+}  // namespace
+
+struct gact_chain_state {
+    ChainBatch batch[GACT_MAX_INFLIGHT];
+    cudaStream_t lane[GACT_MAX_INFLIGHT] = {};       // second stream of a batch: the long-chain lane
+    int head = 0, tail = 0, inflight = 0;
+    int mode = 0;                                    // gact_engine_set_chain_mode
+    int last_mode = 0, last_ctas = 0, last_long = 0; // what the last submit chose (diagnostics)
+};
+
+static void destroy_chain_state(gact_engine *e)
+{
+    if (!e->chains) return;
+    for (int k = 0; k < GACT_MAX_INFLIGHT; k++) {
+        if (e->chains->lane[k]) { cudaStreamSynchronize(e->chains->lane[k]); cudaStreamDestroy(e->chains->lane[k]); }
+        free_chain_batch(e->chains->batch[k]);
+    }
+    delete e->chains;
+    e->chains = nullptr;
+}
+
 extern "C" {
 
 int gact_engine_extend_supported(const gact_engine *e)
@@ -1049,140 +1124,221 @@ int gact_engine_extend_supported(const gact_engine *e)
     return 1;
 }
 
+static gact_chain_state *chain_state(gact_engine *e)
+{
+    if (!e->chains) e->chains = new (std::nothrow) gact_chain_state();
+    return e->chains;
+}
+
 int gact_engine_extend_reserve(gact_engine *e, int n)
 {
     if (!e || n < 0) return GACT_ERR_ARG;
     CU(e, cudaSetDevice(e->device));
-    if ((size_t)n > e->chain_cap) {
-        if (e->d_chain_calls) cudaFree(e->d_chain_calls);
-        if (e->d_chain_res) cudaFree(e->d_chain_res);
-        e->d_chain_calls = nullptr; e->d_chain_res = nullptr; e->chain_cap = 0;
-        if (cudaMalloc(&e->d_chain_calls, (size_t)n * sizeof(ChainCall)) != cudaSuccess ||
-            cudaMalloc(&e->d_chain_res, (size_t)n * sizeof(ChainResult)) != cudaSuccess) {
-            cudaGetLastError();
-            return fail(e, GACT_ERR_NOMEM, "cudaMalloc(chain buffers) failed");
-        }
-        e->chain_cap = (size_t)n;
+    gact_chain_state *cs = chain_state(e);
+    if (!cs) return fail(e, GACT_ERR_NOMEM, "host allocation failed");
+    for (int k = 0; k < GACT_MAX_INFLIGHT; k++) {
+        if (cs->batch[k].busy) continue;
+        int rc = reserve_chain_batch(e, cs->batch[k], (size_t)n);
+        if (rc) return rc;
+        if (!cs->lane[k]) CU(e, cudaStreamCreateWithFlags(&cs->lane[k], cudaStreamNonBlocking));
     }
-    if (!e->ev_c0) { CU(e, cudaEventCreate(&e->ev_c0)); CU(e, cudaEventCreate(&e->ev_c1)); }
+    return GACT_OK;
+}
+
+int gact_engine_set_chain_mode(gact_engine *e, int mode)
+{
+    if (!e || mode < 0 || mode > 4) return GACT_ERR_ARG;
+    gact_chain_state *cs = chain_state(e);
+    if (!cs) return fail(e, GACT_ERR_NOMEM, "host allocation failed");
+    if ((mode == 1 || mode == 2 || mode == 4) && !e->s16h_lat.ok)
+        return fail(e, GACT_ERR_ARG, "the latency chain kernel needs tile_size <= 320 and the one-PRMT score table");
+    cs->mode = mode;
+    return GACT_OK;
+}
+
+int gact_engine_extend_submit(gact_engine *e, int n, const gact_call *calls)
+{
+    if (!e || n < 0 || (n > 0 && !calls)) return GACT_ERR_ARG;
+    if (!gact_engine_extend_supported(e))
+        return fail(e, GACT_ERR_ARG, "on-device extension needs scores in the packed kernels' 16-bit range and ACGT-only sets");
+    if (e->inflight || e->staged) return fail(e, GACT_ERR_STATE, "extend while tile batches are outstanding");
+    gact_chain_state *cs = chain_state(e);
+    if (!cs) return fail(e, GACT_ERR_NOMEM, "host allocation failed");
+    if (cs->inflight >= GACT_MAX_INFLIGHT) return fail(e, GACT_ERR_STATE, "GACT_MAX_INFLIGHT extend batches already in flight");
+    CU(e, cudaSetDevice(e->device));
+    const int slot = cs->head;
+    ChainBatch &b = cs->batch[slot];
+    {
+        int rr = reserve_chain_batch(e, b, (size_t)n);
+        if (rr) return rr;
+        if (!cs->lane[slot]) CU(e, cudaStreamCreateWithFlags(&cs->lane[slot], cudaStreamNonBlocking));
+    }
+    b.n = n;
+    cudaStream_t st = e->cs[slot];
+    CU(e, cudaEventRecord(b.ev_fork, e->stream));           // ordered after what the caller enqueued on the engine's stream
+    CU(e, cudaStreamWaitEvent(st, b.ev_fork, 0));
+    if (n > 0) {
+        const SeqSetHost &rs = e->sets[GACT_SET_REF];
+        const int et = std::max(1, e->params.tile_size - e->params.tile_overlap);
+        // longest query first: a chain is a serial run of tiles, so the long ones must start early or they
+        // are still running alone when every other chain slot has drained.  Counting sort on the expected tile count.
+        b.perm.resize((size_t)n);
+        std::vector<int> est((size_t)n);
+        int est_max = 0;
+        double est_sum = 0.0;
+        for (int i = 0; i < n; i++) {
+            const gact_call &c = calls[i];
+            if (c.query_set >= GACT_MAX_SETS || c.ref_seq < 0 || (size_t)c.ref_seq + 1 >= rs.starts.size())
+                return fail(e, GACT_ERR_ARG, "call " + std::to_string(i) + " out of range");
+            const SeqSetHost &qs = e->sets[c.query_set];
+            if (c.query_seq < 0 || (size_t)c.query_seq + 1 >= qs.starts.size())
+                return fail(e, GACT_ERR_ARG, "call " + std::to_string(i) + " out of range");
+            const long long ql = qs.starts[(size_t)c.query_seq + 1] - qs.starts[(size_t)c.query_seq];
+            const long long rl = rs.starts[(size_t)c.ref_seq + 1] - rs.starts[(size_t)c.ref_seq];
+            if (c.ref_pos < 0 || c.query_pos < 0 || c.ref_pos > rl || c.query_pos > ql)
+                return fail(e, GACT_ERR_ARG, "call " + std::to_string(i) + ": anchor outside its sequences");
+            est[(size_t)i] = (int)std::min<long long>(std::min(ql, rl) / et + 2, 1 << 20);
+            est_max = std::max(est_max, est[(size_t)i]);
+            est_sum += est[(size_t)i];
+        }
+        if (getenv("GACT_CHAIN_NOSORT")) {
+            for (int i = 0; i < n; i++) b.perm[(size_t)i] = i;
+        } else {
+            std::vector<int> start((size_t)est_max + 2, 0);
+            for (int i = 0; i < n; i++) start[(size_t)(est_max - est[(size_t)i]) + 1]++;
+            for (int k = 1; k <= est_max + 1; k++) start[(size_t)k] += start[(size_t)k - 1];
+            for (int i = 0; i < n; i++) b.perm[(size_t)start[(size_t)(est_max - est[(size_t)i])]++] = i;
+        }
+        for (int i = 0; i < n; i++) {
+            const gact_call &c = calls[b.perm[(size_t)i]];
+            const SeqSetHost &qs = e->sets[c.query_set];
+            ChainCall &d = b.h_calls[i];
+            d.ref_start = rs.starts[(size_t)c.ref_seq];
+            d.query_start = qs.starts[(size_t)c.query_seq];
+            d.ref_len = (int)(rs.starts[(size_t)c.ref_seq + 1] - d.ref_start);
+            d.query_len = (int)(qs.starts[(size_t)c.query_seq + 1] - d.query_start);
+            d.ref_pos = c.ref_pos; d.query_pos = c.query_pos;
+            d.query_set = c.query_set; d.pad = 0;
+        }
+        CU(e, cudaMemcpyAsync(b.d_calls, b.h_calls, (size_t)n * sizeof(ChainCall), cudaMemcpyHostToDevice, st));
+        CU(e, cudaEventRecord(b.ev0, st));
+
+        // ---- which mapping ----
+        //   1: latency kernel, one CTA (4 warps = one per SM sub-partition) per SM    2: latency kernel, two CTAs per SM
+        //   3: throughput kernel (two tiles per warp for tile_size <= 320)
+        //   4: split -- the longest chains on the latency kernel (one CTA per SM, own stream), the rest on the throughput kernel
+        // auto: about half of the candidates die in their first tile, so the real load per sub-partition is ~ est_sum / 2 / (4 SMs);
+        // while that stays below the longest chain, the longest chain sets the time and must run alone on its sub-partition.
+        const bool lat_ok = e->s16h_lat.ok;
+        int mode = cs->mode;
+        if (const char *m = getenv("GACT_CHAIN_MODE")) mode = atoi(m);
+        const double per_sub = 0.5 * est_sum / (4.0 * e->num_sms);
+        const double thr_slots = (double)e->s16h.slots();
+        if (mode == 0) {
+            if (!lat_ok) mode = 3;
+            else if (per_sub <= 0.7 * est_max) mode = 1;
+            else if (per_sub <= 1.4 * est_max) mode = 2;
+            else mode = (n > thr_slots) ? 4 : 3;
+        }
+        if (!lat_ok && mode != 3) mode = 3;
+        int n_long = 0;
+        if (mode == 4) {
+            // chains whose serial length exceeds 60 % of the average load per chain slot of the throughput kernel,
+            // at most one per sub-partition
+            const double long_tiles = 0.6 * est_sum / thr_slots;
+            const int cap_long = 4 * e->num_sms;
+            while (n_long < n && n_long < cap_long && (double)est[(size_t)b.perm[(size_t)n_long]] > long_tiles) n_long++;
+            if (n_long < 8) { n_long = 0; mode = 3; }
+        }
+        cs->last_mode = mode; cs->last_long = n_long;
+        const int thr = e->params.first_tile_score_threshold;
+        if (mode == 1 || mode == 2) {
+            int ctas = (mode == 1 ? 1 : 2) * e->num_sms;
+            if (const char *c = getenv("GACT_CHAIN_CTAS")) ctas = atoi(c);
+            cs->last_ctas = ctas;
+            s16h_launch_chain(e->s16h_lat, e->kp, b.d_calls, n, b.d_res, thr, b.d_aux, b.d_taken, st, 2, ctas, e->num_sms);
+            e->stats.kernel_launches++;
+        } else {
+            if (n_long > 0) {
+                CU(e, cudaEventRecord(b.ev_lane, st));
+                CU(e, cudaStreamWaitEvent(cs->lane[slot], b.ev_lane, 0));
+                s16h_launch_chain(e->s16h_lat, e->kp, b.d_calls, n_long, b.d_res, thr, b.d_aux + 1, b.d_taken, cs->lane[slot], 2,
+                                  e->num_sms, e->num_sms);
+                CU(e, cudaGetLastError());
+                CU(e, cudaEventRecord(b.ev_lane, cs->lane[slot]));
+                e->stats.kernel_launches++;
+            }
+            const int n_rest = n - n_long;
+            if (n_rest > 0) {
+                // every chain resident: deal the (sorted) chains round-robin over the CTAs so that the long ones do not
+                // share SMs; with more chains than slots the plain in-order claim measured faster (profiles/r1_chain_order.txt)
+                int deal = (n_rest <= e->s16h.slots()) ? 1 : 0;
+                if (const char *d = getenv("GACT_CHAIN_DEAL")) deal = atoi(d);
+                cs->last_ctas = e->s16h.ctas;
+                s16h_launch_chain(e->s16h, e->kp, b.d_calls + n_long, n_rest, b.d_res + n_long, thr, b.d_aux, b.d_taken + n_long, st,
+                                  deal, e->s16h.ctas, e->num_sms, slot);
+                e->stats.kernel_launches++;
+            }
+            if (n_long > 0) CU(e, cudaStreamWaitEvent(st, b.ev_lane, 0));
+        }
+        CU(e, cudaGetLastError());
+        CU(e, cudaEventRecord(b.ev1, st));
+        CU(e, cudaMemcpyAsync(b.h_res, b.d_res, (size_t)n * sizeof(ChainResult), cudaMemcpyDeviceToHost, st));
+        e->stats.h2d_bytes += (double)n * sizeof(ChainCall);
+        e->stats.d2h_bytes += (double)n * sizeof(ChainResult);
+    }
+    CU(e, cudaEventRecord(b.ev_done, st));
+    b.busy = true;
+    cs->head = (cs->head + 1) % GACT_MAX_INFLIGHT;
+    cs->inflight++;
+    return GACT_OK;
+}
+
+int gact_engine_extend_wait(gact_engine *e, gact_alignment *out)
+{
+    if (!e) return GACT_ERR_ARG;
+    gact_chain_state *cs = e->chains;
+    if (!cs || cs->inflight == 0) return fail(e, GACT_ERR_STATE, "extend_wait without extend_submit");
+    CU(e, cudaSetDevice(e->device));
+    ChainBatch &b = cs->batch[cs->tail];
+    if (b.n > 0 && !out) return GACT_ERR_ARG;
+    CU(e, cudaEventSynchronize(b.ev_done));
+    if (b.n > 0) {
+        float ms = 0.f;
+        CU(e, cudaEventElapsedTime(&ms, b.ev0, b.ev1));
+        e->last_kernel_ms = ms;
+        e->stats.kernel_ms += ms;
+        for (int i = 0; i < b.n; i++) {
+            const ChainResult &r = b.h_res[i];
+            gact_alignment &o = out[b.perm[(size_t)i]];
+            o.ab = r.ab; o.ae = r.ae; o.bb = r.bb; o.be = r.be; o.score = r.score; o.first_tile_score = r.first_tile_score;
+            o.n_tiles = r.n_tiles; o.reserved = 0; o.n_cells = r.n_cells;
+            e->stats.tiles += (uint64_t)r.n_tiles;
+            e->stats.cells += (uint64_t)r.n_cells;
+        }
+    }
+    e->stats.batches++;
+    b.busy = false;
+    cs->tail = (cs->tail + 1) % GACT_MAX_INFLIGHT;
+    cs->inflight--;
     return GACT_OK;
 }
 
 int gact_engine_extend(gact_engine *e, int n, const gact_call *calls, gact_alignment *out)
 {
     if (!e || n < 0 || (n > 0 && (!calls || !out))) return GACT_ERR_ARG;
-    if (!gact_engine_extend_supported(e))
-        return fail(e, GACT_ERR_ARG, "on-device extension needs scores in the packed kernels' 16-bit range and ACGT-only sets");
-    if (e->inflight || e->staged) return fail(e, GACT_ERR_STATE, "extend while batches are outstanding");
-    if (n == 0) return GACT_OK;
-    CU(e, cudaSetDevice(e->device));
-    std::vector<ChainCall> cc((size_t)n);
-    const SeqSetHost &rs = e->sets[GACT_SET_REF];
-    // longest query first: a chain is a serial run of tiles, so the long ones must start early or they
-    // are still running alone when every other chain slot has drained
-    std::vector<int> perm((size_t)n);
-    for (int i = 0; i < n; i++) perm[(size_t)i] = i;
-    {
-        std::vector<int64_t> qlen((size_t)n, 0);
-        for (int i = 0; i < n; i++) {
-            const gact_call &c = calls[i];
-            if (c.query_set < GACT_MAX_SETS && c.query_seq >= 0 && (size_t)c.query_seq + 1 < e->sets[c.query_set].starts.size())
-                qlen[(size_t)i] = e->sets[c.query_set].starts[(size_t)c.query_seq + 1] - e->sets[c.query_set].starts[(size_t)c.query_seq];
-        }
-        if (!getenv("GACT_CHAIN_NOSORT")) std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return qlen[(size_t)a] > qlen[(size_t)b]; });
-    }
-    for (int i = 0; i < n; i++) {
-        const gact_call &c = calls[perm[(size_t)i]];
-        if (c.query_set >= GACT_MAX_SETS || c.ref_seq < 0 || (size_t)c.ref_seq + 1 >= rs.starts.size())
-            return fail(e, GACT_ERR_ARG, "call " + std::to_string(perm[(size_t)i]) + " out of range");
-        const SeqSetHost &qs = e->sets[c.query_set];
-        if (c.query_seq < 0 || (size_t)c.query_seq + 1 >= qs.starts.size())
-            return fail(e, GACT_ERR_ARG, "call " + std::to_string(perm[(size_t)i]) + " out of range");
-        ChainCall &d = cc[(size_t)i];
-        d.ref_start = rs.starts[(size_t)c.ref_seq];
-        d.query_start = qs.starts[(size_t)c.query_seq];
-        d.ref_len = (int)(rs.starts[(size_t)c.ref_seq + 1] - d.ref_start);
-        d.query_len = (int)(qs.starts[(size_t)c.query_seq + 1] - d.query_start);
-        d.ref_pos = c.ref_pos; d.query_pos = c.query_pos;
-        d.query_set = c.query_set; d.pad = 0;
-        if (c.ref_pos < 0 || c.query_pos < 0 || c.ref_pos > d.ref_len || c.query_pos > d.query_len)
-            return fail(e, GACT_ERR_ARG, "call " + std::to_string(perm[(size_t)i]) + ": anchor outside its sequences");
-    }
-    {
-        int rr = gact_engine_extend_reserve(e, n);
-        if (rr) return rr;
-    }
-    if (!e->ev_c0) { CU(e, cudaEventCreate(&e->ev_c0)); CU(e, cudaEventCreate(&e->ev_c1)); }
-    cudaStream_t st = e->stream;
-    Slot &s = e->slots[0];
-    CU(e, cudaMemcpyAsync(e->d_chain_calls, cc.data(), (size_t)n * sizeof(ChainCall), cudaMemcpyHostToDevice, st));
-    CU(e, cudaMemsetAsync(s.d_counters, 0, 2 * sizeof(int), st));
-    CU(e, cudaEventRecord(e->ev_c0, st));
-    // fewer candidates than chain slots: every chain is resident at once and the longest one sets the
-    // time -> use the one-tile-per-warp mapping with its lower per-tile latency
-    const bool latency_mode = e->s16h_lat.ok && n <= e->s16h_lat.ctas * e->s16h_lat.warps_per_cta && !getenv("GACT_CHAIN_THROUGHPUT");
-    // every chain resident in the two-tiles-per-warp mapping: deal the (sorted) chains round-robin over the
-    // CTAs so that the long ones do not share SMs; with more chains than slots the plain in-order claim
-    // measured faster (profiles/r1_chain_order.txt)
-    int deal = (!latency_mode && n <= e->s16h.ctas * e->s16h.warps_per_cta * e->s16h.tpw()) ? 1 : 0;
-    if (getenv("GACT_CHAIN_DEAL")) deal = atoi(getenv("GACT_CHAIN_DEAL"));
-    // More chains than slots: a tile of a resident chain takes ~160 us at full occupancy, so the longest reads
-    // (150 tiles for 30 kb) would outlast the rest of the shard.  The chains whose serial length exceeds 60 % of
-    // the average load per chain slot go to the one-tile-per-warp kernel, launched first on its own stream with
-    // at most one CTA per SM; the two-tiles-per-warp kernel takes the remaining calls and the remaining SM space.
-    int n_long = 0;
-    if (!latency_mode && e->s16h_lat.ok && !(getenv("GACT_CHAIN_LONG") && atoi(getenv("GACT_CHAIN_LONG")) == 0)) {
-        const int et = std::max(1, e->params.tile_size - e->params.tile_overlap);
-        const double slots = (double)e->s16h.ctas * e->s16h.warps_per_cta * e->s16h.tpw();
-        double total = 0.0;
-        for (int i = 0; i < n; i++) total += (double)(cc[(size_t)i].query_len / et + 2);
-        const double long_tiles = 0.6 * total / slots;
-        const int cap_long = e->num_sms * e->s16h_lat.warps_per_cta;
-        while (n_long < n && n_long < cap_long && (double)(cc[(size_t)n_long].query_len / et + 2) > long_tiles) n_long++;
-        if (n_long < 8) n_long = 0;
-    }
-    if (n_long > 0) {
-        Slot &s1 = e->slots[1];
-        CU(e, cudaEventRecord(s1.ev_fork, st));
-        CU(e, cudaStreamWaitEvent(e->cs[1], s1.ev_fork, 0));
-        s16h_launch_chain(e->s16h_lat, e->kp, e->d_chain_calls, n_long, e->d_chain_res, e->params.first_tile_score_threshold,
-                          s.d_counters + 0, e->cs[1], 0);
-        CU(e, cudaGetLastError());
-        CU(e, cudaEventRecord(s1.ev_k1, e->cs[1]));
-        const int n_rest = n - n_long;
-        if (n_rest > 0) {
-            int deal_rest = (n_rest <= e->s16h.ctas * e->s16h.warps_per_cta * e->s16h.tpw()) ? 1 : 0;
-            if (getenv("GACT_CHAIN_DEAL")) deal_rest = atoi(getenv("GACT_CHAIN_DEAL"));
-            s16h_launch_chain(e->s16h, e->kp, e->d_chain_calls + n_long, n_rest, e->d_chain_res + n_long,
-                              e->params.first_tile_score_threshold, s.d_counters + 1, st, deal_rest);
-        }
-        CU(e, cudaStreamWaitEvent(st, s1.ev_k1, 0));
-        e->stats.kernel_launches++;
-    } else {
-        s16h_launch_chain(latency_mode ? e->s16h_lat : e->s16h, e->kp, e->d_chain_calls, n, e->d_chain_res, e->params.first_tile_score_threshold,
-                          s.d_counters + 1, st, deal);
-    }
-    CU(e, cudaGetLastError());
-    CU(e, cudaEventRecord(e->ev_c1, st));
-    std::vector<ChainResult> res((size_t)n);
-    CU(e, cudaMemcpyAsync(res.data(), e->d_chain_res, (size_t)n * sizeof(ChainResult), cudaMemcpyDeviceToHost, st));
-    CU(e, cudaStreamSynchronize(st));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e->ev_c0, e->ev_c1);
-    e->last_kernel_ms = ms;
-    e->stats.kernel_ms += ms;
-    e->stats.kernel_launches++;
-    e->stats.batches++;
-    e->stats.h2d_bytes += (double)n * sizeof(ChainCall);
-    e->stats.d2h_bytes += (double)n * sizeof(ChainResult);
-    for (int i = 0; i < n; i++) {
-        const ChainResult &r = res[(size_t)i];
-        gact_alignment &o = out[perm[(size_t)i]];
-        o.ab = r.ab; o.ae = r.ae; o.bb = r.bb; o.be = r.be; o.score = r.score; o.first_tile_score = r.first_tile_score;
-        o.n_tiles = r.n_tiles; o.reserved = 0; o.n_cells = r.n_cells;
-        e->stats.tiles += (uint64_t)r.n_tiles;
-        e->stats.cells += (uint64_t)r.n_cells;
-    }
+    if (e->chains && e->chains->inflight) return fail(e, GACT_ERR_STATE, "extend while asynchronous extend batches are in flight");
+    int rc = gact_engine_extend_submit(e, n, calls);
+    if (rc) return rc;
+    return gact_engine_extend_wait(e, out);
+}
+
+int gact_engine_chain_info(const gact_engine *e, int *mode, int *ctas, int *n_long)
+{
+    if (!e || !e->chains) return GACT_ERR_ARG;
+    if (mode) *mode = e->chains->last_mode;
+    if (ctas) *ctas = e->chains->last_ctas;
+    if (n_long) *n_long = e->chains->last_long;
     return GACT_OK;
 }
 

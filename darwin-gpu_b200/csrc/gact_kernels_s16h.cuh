@@ -48,9 +48,20 @@ struct DirWinH {
 // Per-segment context and the building blocks shared by the tile kernel, the first-tile kernel and
 // the chain kernel.  Every function below is executed by the WHOLE warp (its shuffles and ballots use
 // the full mask); each 16-lane segment works on its own tile, segments without work pass n = m = 0.
+// Shared-memory bytes of one segment's sequence arrays.  rr[] carries PAD = 2 * LANES sentinel words on the left (rows
+// <= 0: lanes that have not reached row 1 yet run pseudo rows against the sentinel, which reproduce the border values,
+// so the wavefront loop needs no per-lane "am I active" branch) and PAD words of slack on the right (rows past the
+// end of a tile: their results are never used, the words only have to be readable).
+__host__ __device__ constexpr size_t s16h_seq_bytes(int CS, int LANES)
+{
+    const int TS = CS * 2 * LANES, PAD = 2 * LANES;
+    return (size_t)((((PAD + TS + 2 + PAD) * 4 + (TS + 2) * 4) + 15) & ~15) + (size_t)((2 * (TS / 16 + 2) * 4 + 15) & ~15);
+}
+
 template <int CS, int LANES>
 struct SegCtx {
     static constexpr int TS = CS * 2 * LANES;
+    static constexpr int PAD = 2 * LANES;
     int lane, seg, sl, segbase;
     uint32_t *rr;            // rr[i]: substitution table of R[i] (LUT) or enc(R[i]) | enc(R[i-1]) << 16
     uint16_t *qs, *rb;       // enc(Q[j]), enc(R[i])
@@ -60,19 +71,24 @@ struct SegCtx {
     int B, KO, KI, KD, ONE, et, match, mismatch, gap_open, gap_extend;
     uint32_t Bp, ma16, mi16, ge16, borderD_tag, borderD_raw, lut_mis, lut_delta;
 
-    __device__ __forceinline__ void init(const KParams &P, uint8_t *smem, int warp, size_t seq_bytes, uint8_t *gscratch,
-                                         size_t dir_bytes, int global_warp)
+    // seq_stride: bytes between consecutive segments' carve-outs (>= s16h_seq_bytes; the latency chain kernel keeps
+    // the direction window behind the sequence arrays).  gscratch: global scratch of the direction windows or nullptr.
+    template <bool SMEMWIN = false>
+    __device__ __forceinline__ void init(const KParams &P, uint8_t *smem, int warp, size_t seq_stride, uint8_t *gscratch,
+                                         size_t dir_bytes, int global_warp, bool lut)
     {
         asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
         seg = lane / LANES; sl = lane % LANES; segbase = seg * LANES;
         constexpr int TPW = 32 / LANES;
-        uint8_t *my = smem + ((size_t)warp * TPW + seg) * seq_bytes;
-        rr = reinterpret_cast<uint32_t *>(my);
-        qs = reinterpret_cast<uint16_t *>(my + (TS + 2) * 4);
-        rb = reinterpret_cast<uint16_t *>(my + (TS + 2) * 6);
-        wr = reinterpret_cast<uint32_t *>(my + (((TS + 2) * 8 + 15) & ~15));
+        uint8_t *my = smem + ((size_t)warp * TPW + seg) * seq_stride;
+        rr = reinterpret_cast<uint32_t *>(my) + PAD;
+        qs = reinterpret_cast<uint16_t *>(my + (PAD + TS + 2 + PAD) * 4);
+        rb = qs + (TS + 2);
+        wr = reinterpret_cast<uint32_t *>(my + ((((PAD + TS + 2 + PAD) * 4 + (TS + 2) * 4) + 15) & ~15));
         wq = wr + (TS / 16 + 2);
-        dirbase = gscratch ? (void *)(gscratch + ((size_t)global_warp * TPW + seg) * dir_bytes) : nullptr;
+        // direction window: per-segment global scratch, or (SMEMWIN) the shared memory behind this segment's sequence arrays
+        if (SMEMWIN) dirbase = (void *)(my + s16h_seq_bytes(CS, LANES));
+        else dirbase = gscratch ? (void *)(gscratch + ((size_t)global_warp * TPW + seg) * dir_bytes) : nullptr;
         B = P.s16_bias; Bp = pk16(B);
         match = P.match; mismatch = P.mismatch; gap_open = P.gap_open; gap_extend = P.gap_extend; et = P.et;
         ma16 = pk16(P.match * 16); mi16 = pk16(P.mismatch * 16); ge16 = pk16(P.gap_extend * 16);
@@ -84,6 +100,11 @@ struct SegCtx {
         borderD_raw = ((uint32_t)(B + P.gap_open * 16) << 16) | (uint32_t)B;
         lut_mis = (uint32_t)((P.mismatch * 16) & 0xff) * 0x01010101u;
         lut_delta = (uint32_t)(((P.match ^ P.mismatch) * 16) & 0xff);
+        // sentinel rows <= 0 (written once: staging only writes rows >= 1) and defined slack on the right
+        const uint32_t sent = lut ? lut_mis : (SENT_R | (SENT_R << 16));
+        for (int x = sl; x <= PAD; x += LANES) rr[-x] = sent;
+        for (int x = 1 + sl; x < TS + 2 + PAD; x += LANES) rr[x] = sent;
+        __syncwarp();
     }
 };
 
@@ -119,8 +140,8 @@ __device__ __forceinline__ void seg_stage(const SegCtx<CS, LANES> &cx, const Seq
     __syncwarp();
     if (work) {
         const int ro = (int)(ref_off & 15), qo = (int)(query_off & 15);
-        for (int x = cx.sl; x <= n + 1; x += LANES) {
-            const bool in = (x >= 1 && x <= n);
+        for (int x = 1 + cx.sl; x <= n + 1; x += LANES) {
+            const bool in = (x <= n);
             const int base = !in ? 0 : rset.packed ? smem_base(cx.wr, ro, ref_len, reverse, x)
                                                    : tile_base(rset, ref_off, ref_len, reverse, x);
             cx.rb[x] = (uint16_t)(in ? enc_base(base) : SENT_R);
@@ -139,8 +160,8 @@ __device__ __forceinline__ void seg_stage(const SegCtx<CS, LANES> &cx, const Seq
     }
     __syncwarp();
     if (!LUT && work) {
-        for (int x = cx.sl; x <= n + 1; x += LANES)
-            cx.rr[x] = (uint32_t)cx.rb[x] | ((uint32_t)(x >= 1 ? cx.rb[x - 1] : (uint16_t)SENT_R) << 16);
+        for (int x = 1 + cx.sl; x <= n + 1; x += LANES)
+            cx.rr[x] = (uint32_t)cx.rb[x] | ((uint32_t)(x >= 2 ? cx.rb[x - 1] : (uint16_t)SENT_R) << 16);
     }
     __syncwarp();
 }
@@ -163,7 +184,12 @@ __device__ __forceinline__ void seg_load_q(const SegCtx<CS, LANES> &cx, int m, u
     }
 }
 
-// DP of one tile per segment: fills the direction window, returns the corner score H[n][m]
+// DP of one tile per segment: fills the direction window, returns the corner score H[n][m].
+// The wavefront loops carry no per-lane activity test: a lane that has not reached row 1 yet computes pseudo rows
+// <= 0 against the sentinel words left of rr[1] (every score a mismatch: H stays 0, I and D stay at gap_open, which
+// gives row 1 the same values and the same open-flags as the reference's -inf borders, align.cpp:87-97), and a lane
+// past its last row computes rows whose results nobody reads (its stores are predicated off, the corner is taken at
+// the corner cell's own step).
 template <int CS, int LANES, bool LUT>
 __device__ __forceinline__ int seg_dp(const SegCtx<CS, LANES> &cx, const uint32_t (&q)[CS], int n, int m,
                                       const DirWinH<CS> &dw)
@@ -175,20 +201,25 @@ __device__ __forceinline__ int seg_dp(const SegCtx<CS, LANES> &cx, const uint32_
     const int laststrip = (m > 0) ? (m - 1) / CS : -1;
     const int lastlane = laststrip >> 1;                       // segment-local
     const int c_lane = max(lastlane, 0), c_half = laststrip & 1, c_col = (m > 0) ? (m - 1) - laststrip * CS : 0;
-    const int kc = n + 2 * c_lane + c_half;
+    const int kc = n + 2 * c_lane + c_half;                    // step in which the corner cell (n, m) is computed
     const bool work = (n > 0 && m > 0);
-    const int steps_seg = work ? n + 1 + 2 * lastlane : 0;
+    const int steps_seg = work ? kc : 0;                       // no real cell is left after the corner's step
     // the first lane that keeps direction codes (lane0) reaches window row i0 at step i0 + 2*lane0;
     // until then every lane can stay in the cheaper untagged loop
     int steps = steps_seg, k1 = work ? min(dw.i0 - 1 + 2 * dw.lane0, steps_seg) : 0x3fffffff;
+    int kc_min = work ? kc : 0x3fffffff;                       // the corner step of the segment that finishes first
 #pragma unroll
     for (int o = LANES; o < 32; o <<= 1) {
         steps = max(steps, __shfl_xor_sync(FULL, steps, o));
         k1 = min(k1, __shfl_xor_sync(FULL, k1, o));
+        kc_min = min(kc_min, __shfl_xor_sync(FULL, kc_min, o));
     }
     k1 = min(k1, steps);
-    const int kfirst = (work && sl <= lastlane) ? 2 * sl + 1 : 0x3fffffff;
-    const int kstore = (work && sl >= dw.lane0) ? dw.i0 + 2 * sl : 0x3fffffff;
+    kc_min = min(kc_min, steps);
+    // codes are kept from window row i0 on, by the lanes that own window columns, while the lane has real rows
+    const bool keeps = work && sl >= dw.lane0 && sl <= lastlane;
+    const int kstore = keeps ? dw.i0 + 2 * sl : 0x3fffffff;
+    const int kend = keeps ? n + 2 * sl + 1 : -1;            // last step with a real row in either half
     const uint32_t *rrp = cx.rr - 2 * sl;               // rrp[k] = rr[k - 2*sl]
 
     // ---------------- phase 1: rows above every segment's window, score only ----------------
@@ -200,6 +231,7 @@ __device__ __forceinline__ int seg_dp(const SegCtx<CS, LANES> &cx, const uint32_
         IcUp[c] = pk16(S16_NEG, S16_NEG);
     }
     uint32_t eG = Bp, eD = pk16(S16_NEG), diag = Bp;
+    uint32_t rprev = LUT ? rrp[0] : 0u;                 // reference word of the previous step = this step's high half
     int k = 1;
     for (; k <= k1; k++) {
         const uint32_t pack = __byte_perm(eG, eD, 0x7632);
@@ -207,25 +239,24 @@ __device__ __forceinline__ int seg_dp(const SegCtx<CS, LANES> &cx, const uint32_
         if (sl == 0) recv = cx.borderD_raw;
         const uint32_t inG = __byte_perm(recv, eG, 0x5410);
         const uint32_t inD = __byte_perm(recv, eD, 0x5432);
-        if ((unsigned)(k - kfirst) <= (unsigned)n) {
-            const uint32_t rlo = rrp[k], rhi = LUT ? rrp[k - 1] : 0u;
-            uint32_t hd = diag, dv = inD;
+        const uint32_t rlo = rrp[k], rhi = rprev;
+        uint32_t hd = diag, dv = inD;
 #pragma unroll
-            for (int c = 0; c < CS; c++) {
-                const uint32_t sc = subst_score<LUT>(q[c], rlo, rhi, cx.ma16, cx.mi16);
-                const uint32_t mc = __viaddmax_s16x2(hd, sc, Bp);
-                hd = Gup[c];
-                const uint32_t iv = __viaddmax_s16x2(IcUp[c], ge16, IoUp[c]);
-                Gup[c] = __vimax3_s16x2(mc, iv, dv);
-                const uint32_t mo = (uint32_t)((int)mc * cx.ONE + cx.KO);
-                IoUp[c] = mo;
-                IcUp[c] = iv;
-                dv = __viaddmax_s16x2(dv, ge16, mo);
-            }
-            eG = Gup[CS - 1];
-            eD = dv;
-            diag = inG;
+        for (int c = 0; c < CS; c++) {
+            const uint32_t sc = subst_score<LUT>(q[c], rlo, rhi, cx.ma16, cx.mi16);
+            const uint32_t mc = __viaddmax_s16x2(hd, sc, Bp);
+            hd = Gup[c];
+            const uint32_t iv = __viaddmax_s16x2(IcUp[c], ge16, IoUp[c]);
+            Gup[c] = __vimax3_s16x2(mc, iv, dv);
+            const uint32_t mo = (uint32_t)((int)mc * cx.ONE + cx.KO);
+            IoUp[c] = mo;
+            IcUp[c] = iv;
+            dv = __viaddmax_s16x2(dv, ge16, mo);
         }
+        eG = Gup[CS - 1];
+        eD = dv;
+        diag = inG;
+        if (LUT) rprev = rlo;
     }
     // ---------------- switch to the tagged domain ----------------
 #pragma unroll
@@ -239,47 +270,51 @@ __device__ __forceinline__ int seg_dp(const SegCtx<CS, LANES> &cx, const uint32_
     uint32_t *wptr = dw.w + ((k - 2 * sl - dw.i0) * dw.nl + (sl - dw.lane0)) * NW;
     uint16_t *hptr = dw.h + ((k - 2 * sl - dw.i0) * dw.nl + (sl - dw.lane0));
     int corner16 = B;
-    for (; k <= steps; k++) {
+    // the loop stops at the corner step of each segment (at most two different ones per warp) so that the corner
+    // value is picked out of the registers outside the loop
+    for (int stop = kc_min;; stop = steps) {
+    for (; k <= stop; k++) {
         const uint32_t pack = __byte_perm(eG, eD, 0x7632);
         uint32_t recv = __shfl_up_sync(FULL, pack, 1, LANES);
         if (sl == 0) recv = cx.borderD_tag;
         const uint32_t inG = __byte_perm(recv, eG, 0x5410);
         const uint32_t inD = __byte_perm(recv, eD, 0x5432);
-        if ((unsigned)(k - kfirst) <= (unsigned)n) {
-            const uint32_t rlo = rrp[k], rhi = LUT ? rrp[k - 1] : 0u;
-            uint32_t hd = diag, dv = inD;
-            uint32_t acc[NW + 1];
+        const uint32_t rlo = rrp[k], rhi = rprev;
+        uint32_t hd = diag, dv = inD;
+        uint32_t acc[NW + 1];
 #pragma unroll
-            for (int c = 0; c < CS; c++) {
-                const uint32_t sc = subst_score<LUT>(q[c], rlo, rhi, cx.ma16, cx.mi16);
-                const uint32_t mt = __viaddmax_s16x2(hd, sc, Bp) | 0x000f000fu;
-                hd = Gup[c];
-                const uint32_t iv = __viaddmax_s16x2(IcUp[c], ge16, IoUp[c]);
-                const uint32_t g = __vimax3_s16x2(mt, iv, dv);
-                const uint32_t code = (g & 0x000c000cu) | ((iv | dv) & 0x00030003u);
-                if ((c & 3) == 0) acc[c >> 2] = code; else acc[c >> 2] = acc[c >> 2] * 16u + code;
-                Gup[c] = g;
-                IoUp[c] = (uint32_t)((int)mt * cx.ONE + cx.KI);
-                IcUp[c] = iv & 0xfffdfffdu;
-                dv = __viaddmax_s16x2(dv & 0xfffefffeu, ge16, (uint32_t)((int)mt * cx.ONE + cx.KD));
-            }
-            eG = Gup[CS - 1];
-            eD = dv;
-            diag = inG;
-            if (k >= kstore) {
+        for (int c = 0; c < CS; c++) {
+            const uint32_t sc = subst_score<LUT>(q[c], rlo, rhi, cx.ma16, cx.mi16);
+            const uint32_t mt = __viaddmax_s16x2(hd, sc, Bp) | 0x000f000fu;
+            hd = Gup[c];
+            const uint32_t iv = __viaddmax_s16x2(IcUp[c], ge16, IoUp[c]);
+            const uint32_t g = __vimax3_s16x2(mt, iv, dv);
+            const uint32_t code = (g & 0x000c000cu) | ((iv | dv) & 0x00030003u);
+            if ((c & 3) == 0) acc[c >> 2] = code; else acc[c >> 2] = acc[c >> 2] * 16u + code;
+            Gup[c] = g;
+            IoUp[c] = (uint32_t)((int)mt * cx.ONE + cx.KI);
+            IcUp[c] = iv & 0xfffdfffdu;
+            dv = __viaddmax_s16x2(dv & 0xfffefffeu, ge16, (uint32_t)((int)mt * cx.ONE + cx.KD));
+        }
+        eG = Gup[CS - 1];
+        eD = dv;
+        diag = inG;
+        if (LUT) rprev = rlo;
+        if (k >= kstore && k <= kend) {
 #pragma unroll
-                for (int x = 0; x < NW; x++) wptr[x] = acc[x];
-                if (R) *hptr = (uint16_t)((acc[NW] & 0xffu) | ((acc[NW] >> 8) & 0xff00u));
-            }
-            if (k == kc) {
-                uint32_t gsel = 0;
-#pragma unroll
-                for (int c = 0; c < CS; c++) if (c == c_col) gsel = Gup[c];
-                corner16 = (int)(short)(c_half ? (gsel >> 16) : (gsel & 0xffffu));
-            }
+            for (int x = 0; x < NW; x++) wptr[x] = acc[x];
+            if (R) *hptr = (uint16_t)((acc[NW] & 0xffu) | ((acc[NW] >> 8) & 0xff00u));
         }
         wptr += dw.nl * NW;
         hptr += dw.nl;
+    }
+        if (work && kc == stop) {
+            uint32_t gsel = 0;
+#pragma unroll
+            for (int c = 0; c < CS; c++) if (c == c_col) gsel = Gup[c];
+            corner16 = (int)(short)(c_half ? (gsel >> 16) : (gsel & 0xffffu));
+        }
+        if (stop >= steps) break;
     }
     int corner = (__shfl_sync(FULL, corner16, cx.segbase + c_lane) - B) >> 4;
     if (!work) corner = 0;
@@ -377,7 +412,6 @@ __device__ __forceinline__ void seg_first_pass(const SegCtx<CS, LANES> &cx, cons
     int steps = work ? n + 1 + 2 * lastlane : 0;
 #pragma unroll
     for (int o = LANES; o < 32; o <<= 1) steps = max(steps, __shfl_xor_sync(FULL, steps, o));
-    const int kfirst = (work && sl <= lastlane) ? 2 * sl + 1 : 0x3fffffff;
     const uint32_t *rrp = cx.rr - 2 * sl;
 
     uint32_t Gup[CS], IoUp[CS], IcUp[CS], best[CS], brow[CS];
@@ -390,6 +424,8 @@ __device__ __forceinline__ void seg_first_pass(const SegCtx<CS, LANES> &cx, cons
         brow[c] = 0;
     }
     uint32_t eG = Bp, eD = pk16(S16_NEG), diag = Bp;
+    uint32_t rprev = LUT ? rrp[0] : 0u;
+    // no per-lane activity branch (see seg_dp): rows outside 1..n are masked out of the maximum search by `keep`
     for (int k = 1; k <= steps; k++) {
         const uint32_t pack = __byte_perm(eG, eD, 0x7632);
         uint32_t recv = __shfl_up_sync(FULL, pack, 1, LANES);
@@ -397,33 +433,32 @@ __device__ __forceinline__ void seg_first_pass(const SegCtx<CS, LANES> &cx, cons
         const uint32_t inG = __byte_perm(recv, eG, 0x5410);
         const uint32_t inD = __byte_perm(recv, eD, 0x5432);
         const int ilo = k - 2 * sl;
-        if ((unsigned)(k - kfirst) <= (unsigned)n) {
-            const uint32_t rlo = rrp[k], rhi = LUT ? rrp[k - 1] : 0u;
-            // rows that do not exist (low half: row n+1, high half: row 0) must not be recorded
-            const uint32_t keep = ((ilo <= n) ? 0x0000ffffu : 0u) | ((ilo >= 2) ? 0xffff0000u : 0u);
-            const uint32_t ipair = pk16(ilo, ilo - 1);
-            uint32_t hd = diag, dv = inD;
+        const uint32_t rlo = rrp[k], rhi = rprev;
+        // low half: row ilo, high half: row ilo - 1; only rows 1..n are recorded
+        const uint32_t keep = (((unsigned)(ilo - 1) < (unsigned)n) ? 0x0000ffffu : 0u) | (((unsigned)(ilo - 2) < (unsigned)n) ? 0xffff0000u : 0u);
+        const uint32_t ipair = pk16(ilo, ilo - 1);
+        uint32_t hd = diag, dv = inD;
 #pragma unroll
-            for (int c = 0; c < CS; c++) {
-                const uint32_t sc = subst_score<LUT>(q[c], rlo, rhi, cx.ma16, cx.mi16);
-                const uint32_t mc = __viaddmax_s16x2(hd, sc, Bp);
-                hd = Gup[c];
-                const uint32_t iv = __viaddmax_s16x2(IcUp[c], ge16, IoUp[c]);
-                const uint32_t h = __vimax3_s16x2(mc, iv, dv);
-                Gup[c] = h;
-                const uint32_t mo = (uint32_t)((int)mc * cx.ONE + cx.KO);
-                IoUp[c] = mo;
-                IcUp[c] = iv;
-                dv = __viaddmax_s16x2(dv, ge16, mo);
-                bool ph, pl;
-                best[c] = __vibmax_s16x2(h & keep, best[c], &ph, &pl);      // pred = (h >= best): last maximum wins
-                if (pl) brow[c] = __byte_perm(brow[c], ipair, 0x3254);
-                if (ph) brow[c] = __byte_perm(brow[c], ipair, 0x7610);
-            }
-            eG = Gup[CS - 1];
-            eD = dv;
-            diag = inG;
+        for (int c = 0; c < CS; c++) {
+            const uint32_t sc = subst_score<LUT>(q[c], rlo, rhi, cx.ma16, cx.mi16);
+            const uint32_t mc = __viaddmax_s16x2(hd, sc, Bp);
+            hd = Gup[c];
+            const uint32_t iv = __viaddmax_s16x2(IcUp[c], ge16, IoUp[c]);
+            const uint32_t h = __vimax3_s16x2(mc, iv, dv);
+            Gup[c] = h;
+            const uint32_t mo = (uint32_t)((int)mc * cx.ONE + cx.KO);
+            IoUp[c] = mo;
+            IcUp[c] = iv;
+            dv = __viaddmax_s16x2(dv, ge16, mo);
+            bool ph, pl;
+            best[c] = __vibmax_s16x2(h & keep, best[c], &ph, &pl);      // pred = (h >= best): last maximum wins
+            if (pl) brow[c] = __byte_perm(brow[c], ipair, 0x3254);
+            if (ph) brow[c] = __byte_perm(brow[c], ipair, 0x7610);
         }
+        eG = Gup[CS - 1];
+        eD = dv;
+        diag = inG;
+        if (LUT) rprev = rlo;
     }
     // best cell of this lane by (H, i, j); i, j <= 1024 take 11 bits each
     long long key = -1;
@@ -453,7 +488,7 @@ gact_tile_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *_
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int TPW = 32 / LANES;
     SegCtx<CS, LANES> cx;
-    cx.init(P, smem, threadIdx.x >> 5, seq_bytes, gscratch, dir_bytes, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+    cx.init(P, smem, threadIdx.x >> 5, seq_bytes, gscratch, dir_bytes, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), LUT);
     const int lane = cx.lane, seg = cx.seg, sl = cx.sl;
 
     for (;;) {
@@ -516,7 +551,7 @@ gact_first_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int TPW = 32 / LANES;
     SegCtx<CS, LANES> cx;
-    cx.init(P, smem, threadIdx.x >> 5, seq_bytes, nullptr, 0, 0);
+    cx.init(P, smem, threadIdx.x >> 5, seq_bytes, nullptr, 0, 0, LUT);
     const int lane = cx.lane, seg = cx.seg, sl = cx.sl;
 
     for (;;) {
@@ -574,16 +609,53 @@ __device__ unsigned long long g_chain_prof[8];
 #define PROF_FLUSH(cond)
 #endif
 
-template <int CS, int LANES>
-__global__ void __launch_bounds__(128, (CS <= 10 ? 3 : 2))
+// Claim bookkeeping of one chain-kernel launch (cleared before every launch).  Calls arrive sorted by
+// expected serial length, longest first.  The first claim of every segment is DEALT (a fixed rank per
+// segment, so that the longest chains start at once and spread over the machine); later claims take
+// the next rank from a queue.  A dealt rank that no segment came for (CTA placement is the hardware's
+// choice) is picked up by the scan at the end; `taken` makes every rank run exactly once either way.
+//   deal 0: queue only.
+//   deal 1: rank = segment-in-CTA * gridDim + blockIdx: consecutive ranks go to different CTAs.
+//   deal 2: rank = sm + n_sm * (warp + warps_per_cta * cta_slot_on_that_sm): the 4 * n_sm longest chains each get an
+//           SM sub-partition (one warp scheduler and its ALU pipe) of their own -- a lone warp runs a tile in about a third of
+//           the time it takes with three neighbours (profiles/r2_chain_latency_anatomy_before.txt).  The SM is
+//           identified by %smid, mapped to a dense index in arrival order.
+struct ChainAux {
+    int q_next;               // queue: next undealt rank - q0
+    int scan_next;            // final scan over the dealt ranks [0, q0)
+    int n_vsm;                // deal 2: dense SM indices handed out so far
+    int pad;
+    int vmap[1024];           // deal 2: %smid -> dense index + 1 (0: none yet, -1: being assigned)
+    int sm_slots[1024];       // deal 2: CTAs that have arrived per dense SM index
+};
+
+__device__ __forceinline__ int chain_claim(ChainAux *aux, int *taken, int n_calls, int q0)
+{
+    for (;;) {
+        const int r = q0 + atomicAdd(&aux->q_next, 1);
+        if (r >= n_calls) break;
+        return r;                                  // ranks >= q0 are never dealt
+    }
+    for (;;) {
+        const int r = atomicAdd(&aux->scan_next, 1);
+        if (r >= q0) return n_calls;
+        if (atomicExch(&taken[r], 1) == 0) return r;
+    }
+}
+
+// SMEMWIN: the direction window lives in shared memory behind the segment's sequence arrays (latency
+// mapping, tile_size <= 320: the traceback's dependent loads take ~30 cycles instead of an L2 round trip).
+template <int CS, int LANES, bool SMEMWIN>
+__global__ void __launch_bounds__(128, (SMEMWIN ? 2 : (CS <= 10 ? 3 : 2)))
 gact_chain_s16h_kernel(const __grid_constant__ KParams P, const ChainCall *__restrict__ calls, int n_calls,
-                       ChainResult *__restrict__ results, int thr, int *counter, size_t seq_bytes,
-                       uint8_t *gscratch, size_t dir_bytes, int deal)
+                       ChainResult *__restrict__ results, int thr, ChainAux *aux, int *taken, size_t seq_stride,
+                       uint8_t *gscratch, size_t dir_bytes, int deal, int q0, int n_sm)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr unsigned SEGBITS = (LANES == 32) ? 0xffffffffu : ((1u << LANES) - 1u);
     SegCtx<CS, LANES> cx;
-    cx.init(P, smem, threadIdx.x >> 5, seq_bytes, gscratch, dir_bytes, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+    cx.template init<SMEMWIN>(P, smem, threadIdx.x >> 5, seq_stride, gscratch, dir_bytes,
+                              blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), true);
     const int sl = cx.sl;
     const unsigned segmask = SEGBITS << cx.segbase;
     const int T = P.tile_size;
@@ -597,10 +669,28 @@ gact_chain_s16h_kernel(const __grid_constant__ KParams P, const ChainCall *__res
     long long n_cells = 0;
     int phase = 2, first_tile = 0, prev_gap = 0, anchor_gap = 0, left_any = 0, adv = 1;
     bool alive = true;                       // false once the queue is empty for this segment
-    bool first_claim = deal != 0;
     constexpr int SEGS = 32 / LANES;
     const int lseg = (threadIdx.x >> 5) * SEGS + cx.segbase / LANES;
-    const int n_first = deal ? (int)gridDim.x * (int)(blockDim.x >> 5) * SEGS : 0;   // calls dealt by the fixed first claims
+    // the rank dealt to this segment (-1: none)
+    int dealt = -1;
+    if (deal == 1) dealt = lseg * (int)gridDim.x + (int)blockIdx.x;
+    if (deal == 2) {
+        __shared__ int s_rank0;
+        if (threadIdx.x == 0) {
+            unsigned sm;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+            sm &= 1023u;
+            int v = atomicCAS(&aux->vmap[sm], 0, -1);
+            if (v == 0) { v = atomicAdd(&aux->n_vsm, 1) + 1; atomicExch(&aux->vmap[sm], v); }
+            else while (v < 0) v = atomicAdd(&aux->vmap[sm], 0);          // the assigning thread is already running
+            v = (v - 1) & 1023;
+            const int slot = atomicAdd(&aux->sm_slots[v], 1);
+            s_rank0 = v + n_sm * (int)(blockDim.x >> 5) * SEGS * slot;
+        }
+        __syncthreads();
+        dealt = s_rank0 + n_sm * lseg;
+    }
+    bool first_claim = deal != 0;
     PROF_DECL;
 
     for (;;) {
@@ -616,18 +706,13 @@ gact_chain_s16h_kernel(const __grid_constant__ KParams P, const ChainCall *__res
                     r.n_tiles = n_tiles; r.pad = 0; r.n_cells = n_cells;
                     results[call] = r;
                 }
-                // calls arrive longest first.  The first claim of every segment is fixed so that the longest
-                // chains are dealt round-robin over the CTAs (and hence SMs) instead of filling CTA 0 first;
-                // later claims take the next call in order.
                 int nxt = n_calls;
-                if (first_claim) {
-                    first_claim = false;
-                    nxt = lseg * (int)gridDim.x + (int)blockIdx.x;
+                if (sl == 0) {
+                    if (first_claim && dealt >= 0 && dealt < q0 && atomicExch(&taken[dealt], 1) == 0) nxt = dealt;
+                    else nxt = chain_claim(aux, taken, n_calls, q0);
                 }
-                if (nxt >= n_calls) {
-                    if (sl == 0) nxt = n_first + atomicAdd(counter, 1);
-                    nxt = __shfl_sync(segmask, nxt, cx.segbase);
-                }
+                first_claim = false;
+                nxt = __shfl_sync(segmask, nxt, cx.segbase);
                 if (nxt >= n_calls) { alive = false; call = -1; break; }
                 call = nxt;
                 c = calls[call];
@@ -729,16 +814,19 @@ struct S16HPlan {
     bool ok = false;
     int CS = 0, lanes = 16, win_rows = 0, win_lanes = 0, warps_per_cta = 4, ctas = 0, bias = 0;
     bool lut_ok = false;
+    bool smem_window = false;            // latency chain plan: direction window in shared memory
     size_t seq_bytes = 0, smem = 0, dir_bytes = 0;
     uint8_t *d_scratch = nullptr;        // GACT_MAX_INFLIGHT regions of scratch_bytes: kernels of consecutive batches may overlap
     size_t scratch_bytes = 0;
     int tpw() const { return 32 / lanes; }
+    int slots() const { return ctas * warps_per_cta * tpw(); }       // tiles / chains resident at once
 };
 
 typedef void (*s16h_fn)(const KParams, const gact_tile_desc *, const int *, int, const EffLen *, gact_tile_result *,
                         uint32_t *, int, int *, size_t, uint8_t *, size_t);
 typedef void (*s16h_first_fn)(const KParams, const gact_tile_desc *, const int *, int, EffLen *, int *, size_t);
-typedef void (*s16h_chain_fn)(const KParams, const ChainCall *, int, ChainResult *, int, int *, size_t, uint8_t *, size_t, int);
+typedef void (*s16h_chain_fn)(const KParams, const ChainCall *, int, ChainResult *, int, ChainAux *, int *, size_t, uint8_t *,
+                              size_t, int, int, int);
 
 // (strip width, lanes per tile): T <= 256: (8,16), <= 320: (10,16), <= 512: (8,32), <= 1024: (16,32)
 #define S16H_DISPATCH(CSV, LANESV, EXPR_CS_LANES)                         \
@@ -765,13 +853,12 @@ inline s16h_first_fn s16h_pick_first(int CS, int lanes, bool lut)
 #undef S16H_X
     return f;
 }
-inline s16h_chain_fn s16h_pick_chain(int CS, int lanes)
+inline s16h_chain_fn s16h_pick_chain(int CS, int lanes, bool smem_window)
 {
-    // latency variants of the chain kernel: one tile per warp also for tile_size <= 320
-    if (CS == 4 && lanes == 32) return gact_chain_s16h_kernel<4, 32>;
-    if (CS == 5 && lanes == 32) return gact_chain_s16h_kernel<5, 32>;
+    // latency variants of the chain kernel: one tile per warp also for tile_size <= 320, window in shared memory
+    if (smem_window) return CS == 4 ? gact_chain_s16h_kernel<4, 32, true> : gact_chain_s16h_kernel<5, 32, true>;
     s16h_chain_fn f = nullptr;
-#define S16H_X(C, L) f = gact_chain_s16h_kernel<C, L>
+#define S16H_X(C, L) f = gact_chain_s16h_kernel<C, L, false>
     S16H_DISPATCH(CS, lanes, S16H_X);
 #undef S16H_X
     return f;
@@ -794,9 +881,9 @@ inline void s16h_free_plan(S16HPlan *pl)
 }
 
 // Two tiles per warp for tile_size <= 320, one tile per warp up to 1024.
-// latency = true: plan for the chain kernel only, one tile per warp at every tile size (lower
-// per-tile latency, about 20 % lower throughput): used when a shard has fewer candidates than the GPU
-// has chain slots, so that the longest read's serial tile chain finishes sooner.
+// latency = true: plan for the chain kernel only, tile_size <= 320: one tile per warp (32 lanes, strips of 4 / 5
+// columns) with the direction window in shared memory and two CTAs (8 warps) per SM at most: used when a shard has
+// few candidates, so that the longest read's serial tile chain finishes sooner.
 inline int s16h_make_plan(const gact_params &p, int num_sms, int warps_per_sm, S16HPlan *pl, bool latency = false)
 {
     s16h_free_plan(pl);
@@ -812,32 +899,38 @@ inline int s16h_make_plan(const gact_params &p, int num_sms, int warps_per_sm, S
     if (T <= 256) { CS = 8; lanes = 16; } else if (T <= 320) { CS = 10; lanes = 16; }
     else if (T <= 512) { CS = 8; lanes = 32; } else { CS = 16; lanes = 32; }
     if (latency) {
-        if (T > 320) return 0;                       // already one tile per warp
+        if (T > 320 || !pl->lut_ok) return 0;        // larger tiles already run one per warp; their window does not fit
         CS = (T <= 256) ? 4 : 5; lanes = 32;
+        pl->smem_window = true;
     }
     pl->CS = CS; pl->lanes = lanes;
     pl->win_rows = (et + 1 < T) ? et + 1 : T;
     int wl = et / (2 * CS) + 2;
     pl->win_lanes = wl > lanes ? lanes : wl;
-    const int TS = CS * 2 * lanes;
-    pl->seq_bytes = (size_t)(((TS + 2) * 8 + 15) & ~15) + (size_t)((2 * (TS / 16 + 2) * 4 + 15) & ~15);
+    pl->seq_bytes = s16h_seq_bytes(CS, lanes);
     pl->dir_bytes = s16h_dir_bytes(CS, pl->win_rows, pl->win_lanes);
     int wps = warps_per_sm > 0 ? warps_per_sm : 16;
-    const int wps_max = (CS <= 10) ? 16 : 8;
+    const int wps_max = latency ? 8 : (CS <= 10) ? 16 : 8;
     if (wps > wps_max) wps = wps_max;
     pl->warps_per_cta = 4;
     const int c = (wps + 3) / 4;
     pl->ctas = c * num_sms;
-    pl->smem = (size_t)pl->warps_per_cta * pl->tpw() * pl->seq_bytes;
-    pl->scratch_bytes = (size_t)pl->ctas * pl->warps_per_cta * pl->tpw() * pl->dir_bytes;
-    if (cudaMalloc(&pl->d_scratch, (latency ? 1 : GACT_MAX_INFLIGHT) * pl->scratch_bytes) != cudaSuccess) { cudaGetLastError(); pl->d_scratch = nullptr; return 0; }
+    if (latency) {
+        pl->seq_bytes += pl->dir_bytes;               // stride between the warps' carve-outs: sequences, then the window
+        pl->smem = (size_t)pl->warps_per_cta * pl->seq_bytes;
+        if (pl->smem > 113 * 1024) return 0;          // two CTAs per SM must fit
+    } else {
+        pl->smem = (size_t)pl->warps_per_cta * pl->tpw() * pl->seq_bytes;
+        pl->scratch_bytes = (size_t)pl->ctas * pl->warps_per_cta * pl->tpw() * pl->dir_bytes;
+        if (cudaMalloc(&pl->d_scratch, GACT_MAX_INFLIGHT * pl->scratch_bytes) != cudaSuccess) { cudaGetLastError(); pl->d_scratch = nullptr; return 0; }
+    }
     for (int lut = 0; lut < 2 && !latency; lut++)
         if (cudaFuncSetAttribute((const void *)s16h_pick(CS, lanes, lut != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)pl->smem) != cudaSuccess ||
             cudaFuncSetAttribute((const void *)s16h_pick_first(CS, lanes, lut != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)pl->smem) != cudaSuccess)
             return -1;
-    if (cudaFuncSetAttribute((const void *)s16h_pick_chain(CS, lanes), cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute((const void *)s16h_pick_chain(CS, lanes, pl->smem_window), cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)pl->smem) != cudaSuccess)
         return -1;
     pl->ok = true;
@@ -851,15 +944,29 @@ inline int s16h_grid(const S16HPlan &pl, int n_items)
     return need < pl.ctas ? need : pl.ctas;
 }
 
+// One chain-kernel launch.  aux / taken: claim bookkeeping of this launch (cleared here); grid_ctas: CTAs to launch
+// (<= pl.ctas); deal: see ChainAux; scratch_region: which third of the plan's direction-window scratch to use.
 inline void s16h_launch_chain(const S16HPlan &pl, KParams kp, const ChainCall *calls, int n_calls, ChainResult *results,
-                              int thr, int *counter, cudaStream_t st, int deal = 1)
+                              int thr, ChainAux *aux, int *taken, cudaStream_t st, int deal, int grid_ctas, int num_sms,
+                              int scratch_region = 0)
 {
     kp.win_rows = pl.win_rows;
     kp.win_lanes = pl.win_lanes;
     kp.s16_bias = pl.bias;
     kp.one = 1;
-    s16h_pick_chain(pl.CS, pl.lanes)<<<s16h_grid(pl, n_calls), pl.warps_per_cta * 32, pl.smem, st>>>(
-        kp, calls, n_calls, results, thr, counter, pl.seq_bytes, pl.d_scratch, pl.dir_bytes, deal);
+    const int per_cta = pl.warps_per_cta * pl.tpw();
+    int grid = grid_ctas < 1 ? 1 : grid_ctas;
+    if (grid > pl.ctas) grid = pl.ctas;
+    const int need = (n_calls + per_cta - 1) / per_cta;
+    if (need < grid) grid = need;
+    const long long dealt = deal ? (long long)grid * per_cta : 0;
+    const int q0 = (int)(dealt < n_calls ? dealt : n_calls);
+    cudaMemsetAsync(aux, 0, sizeof(ChainAux), st);
+    if (q0 > 0) cudaMemsetAsync(taken, 0, (size_t)q0 * sizeof(int), st);
+    s16h_pick_chain(pl.CS, pl.lanes, pl.smem_window)<<<grid, pl.warps_per_cta * 32, pl.smem, st>>>(
+        kp, calls, n_calls, results, thr, aux, taken, pl.seq_bytes,
+        pl.d_scratch ? pl.d_scratch + (size_t)scratch_region * pl.scratch_bytes : nullptr, pl.dir_bytes, deal, q0,
+        grid < num_sms ? grid : num_sms);
 }
 
 inline void s16h_launch_first(const S16HPlan &pl, KParams kp, const gact_tile_desc *descs, const int *first_list,

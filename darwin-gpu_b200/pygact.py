@@ -55,6 +55,7 @@ EXPORTS = [
     "gact_engine_last_kernel_ms", "gact_engine_stats", "gact_engine_reset_stats",
     "gact_engine_set_kernel", "gact_engine_get_kernel", "gact_int_peak",
     "gact_engine_extend", "gact_engine_extend_supported", "gact_engine_extend_reserve", "gact_dsoft_reserve",
+    "gact_engine_extend_submit", "gact_engine_extend_wait", "gact_engine_set_chain_mode", "gact_engine_chain_info",
     "gact_dsoft_create", "gact_dsoft_destroy", "gact_dsoft_run", "gact_dsoft_last_kernel_ms",
     "gact_seed_table_build", "gact_seed_table_destroy", "gact_seed_table_info", "gact_seed_table_download",
     "gact_dsoft_create_from_table",
@@ -131,6 +132,14 @@ def load():
     L.gact_engine_extend.argtypes = [vp, i32, vp, vp]
     L.gact_engine_extend_supported.restype = i32
     L.gact_engine_extend_supported.argtypes = [vp]
+    L.gact_engine_extend_submit.restype = i32
+    L.gact_engine_extend_submit.argtypes = [vp, i32, vp]
+    L.gact_engine_extend_wait.restype = i32
+    L.gact_engine_extend_wait.argtypes = [vp, vp]
+    L.gact_engine_set_chain_mode.restype = i32
+    L.gact_engine_set_chain_mode.argtypes = [vp, i32]
+    L.gact_engine_chain_info.restype = i32
+    L.gact_engine_chain_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.gact_dsoft_create.restype = i32
     L.gact_dsoft_create.argtypes = [C.POINTER(vp), vp, vp, C.c_uint64, vp, C.c_uint64, i32, i32, C.c_uint32,
                                     C.c_uint32, i32, i32, i32]
@@ -294,6 +303,25 @@ class GactEngine:
         out = np.zeros(len(calls), dtype=ALIGNMENT_DTYPE)
         self._ck(self.L.gact_engine_extend(self.h, len(calls), calls.ctypes.data, out.ctypes.data), "gact_engine_extend")
         return out
+
+    def extend_submit(self, calls):
+        calls = np.ascontiguousarray(calls, dtype=CALL_DTYPE)
+        self._ck(self.L.gact_engine_extend_submit(self.h, len(calls), calls.ctypes.data), "gact_engine_extend_submit")
+        self._ext_n = getattr(self, "_ext_n", []) + [len(calls)]
+
+    def extend_wait(self):
+        n = self._ext_n.pop(0) if getattr(self, "_ext_n", None) else 0
+        out = np.zeros(n, dtype=ALIGNMENT_DTYPE)
+        self._ck(self.L.gact_engine_extend_wait(self.h, out.ctypes.data), "gact_engine_extend_wait")
+        return out
+
+    def set_chain_mode(self, mode):
+        self._ck(self.L.gact_engine_set_chain_mode(self.h, mode), "gact_engine_set_chain_mode")
+
+    def chain_info(self):
+        m, c, l = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._ck(self.L.gact_engine_chain_info(self.h, C.byref(m), C.byref(c), C.byref(l)), "gact_engine_chain_info")
+        return {"mode": m.value, "ctas": c.value, "n_long": l.value}
 
     def stats(self):
         s = Stats()

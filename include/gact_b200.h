@@ -234,9 +234,21 @@ typedef struct {
 } gact_alignment;
 
 int gact_engine_extend(gact_engine *e, int n, const gact_call *calls, gact_alignment *out);
-/* Optional: allocate the device buffers for up to n calls now (e.g. before a timed phase). */
+/* Asynchronous form: up to GACT_MAX_INFLIGHT batches between submit and wait, each on its own stream, so the
+ * chains of one batch of reads run while the next batch is being filtered (gact_dsoft_submit) and the previous
+ * one is being written out.  wait returns the oldest outstanding batch, out[i] belonging to calls[i] of its submit. */
+int gact_engine_extend_submit(gact_engine *e, int n, const gact_call *calls);
+int gact_engine_extend_wait(gact_engine *e, gact_alignment *out);
+/* Optional: allocate the device buffers for up to n calls per batch now (e.g. before a timed phase). */
 int gact_engine_extend_reserve(gact_engine *e, int n);
 int gact_engine_extend_supported(const gact_engine *e);      /* 1 / 0 */
+/* How chains are mapped onto the GPU (for tests and benchmarks; the result never depends on it):
+ * 0 = auto (from the number and expected length of the chains), 1 = latency kernel (one tile per warp, direction
+ * window in shared memory, tile_size <= 320) with one warp per SM sub-partition, 2 = the same with two,
+ * 3 = throughput kernel (two tiles per warp for tile_size <= 320), 4 = the longest chains on the latency kernel,
+ * the rest on the throughput kernel.  gact_engine_chain_info reports what the last submit used. */
+int gact_engine_set_chain_mode(gact_engine *e, int mode);
+int gact_engine_chain_info(const gact_engine *e, int *mode, int *ctas, int *n_long);
 
 /* ---- D-SOFT candidate filter on the device (seed_pos_table.cpp:100-167, ntcoding.cpp:155-182) ----
  * The seed-position table (index_table_: 4^k + 1 entries, pos_table_) is built by the host

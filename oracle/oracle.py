@@ -105,6 +105,29 @@ def ref_lib():
     return _ref
 
 
+REF_GPU_SO = os.path.join(HERE, "_ref", "libalign_ref_gpu.so")
+_ref_gpu = None
+
+
+def ref_gpu_available():
+    return os.path.exists(REF_GPU_SO)
+
+
+def ref_gpu_lib():
+    """The reference's own GPU tile path (cuda_host.cu + cuda_header.h) built for sm_100a (oracle/ref_gpu_shim.cu)."""
+    global _ref_gpu
+    if _ref_gpu is None:
+        L = C.CDLL(REF_GPU_SO)
+        L.ref_gpu_init.restype = C.c_int
+        L.ref_gpu_init.argtypes = [C.c_int] * 8
+        L.ref_gpu_close.restype = None
+        L.ref_gpu_align_batch.restype = C.c_longlong
+        L.ref_gpu_align_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                          C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        _ref_gpu = L
+    return _ref_gpu
+
+
 def align_tile(ref, query, scores=(1, -1, -1, -1), reverse=0, first=0, et=200):
     """Oracle for one tile.  Returns the reference's queue layout as a list:
     [score, (max_i, max_j if first), states...]  (align.cpp:190-199,208)."""

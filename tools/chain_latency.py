@@ -45,7 +45,7 @@ with G.GactEngine(max_tiles=1024) as eng:
         ms = float(np.median(times[1:]))
         tiles = int(out["n_tiles"][0])
         line = (f"copies {n:5d} read {len(q)} bases tiles/chain {tiles} kernel_ms {ms:.3f} us_per_tile {1e3 * ms / tiles:.2f} "
-                f"score {int(out['score'][0])} mode {os.environ.get('GACT_CHAIN_THROUGHPUT', '0')}")
+                f"score {int(out['score'][0])} chain_info {eng.chain_info()}")
         if prof:
             buf = (C.c_ulonglong * 8)()
             L_.gact_prof_read(buf)

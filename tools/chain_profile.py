@@ -45,9 +45,10 @@ with G.GactEngine(max_tiles=1024) as eng:
     for _ in range(7):
         out = eng.extend(calls)
         times.append(eng.last_kernel_ms())
+    info = eng.chain_info()
     chain_ms = float(np.median(times[1:]))
     chain_min = min(times[1:])
     ds.close()
 cells = int(out["n_cells"].sum())
-print(f"reads {len(reads)} strand-queries {len(sets)} candidates {len(cands)} dsoft_kernel_ms {dsoft_ms:.3f} "
+print(f"chain_info {info} reads {len(reads)} strand-queries {len(sets)} candidates {len(cands)} dsoft_kernel_ms {dsoft_ms:.3f} "
       f"chain_kernel_ms {chain_ms:.3f} (min {chain_min:.3f}) tiles {int(out['n_tiles'].sum())} cells {cells} chain_gcups {cells / chain_ms / 1e6:.1f}")
