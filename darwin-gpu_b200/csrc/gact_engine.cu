@@ -784,21 +784,80 @@ int gact_engine_get_kernel(const gact_engine *e)
 
 // ===========================================================================
 // D-SOFT on the device
+namespace {
+// one set of query / candidate buffers: two of them, so that the next batch of reads can be filtered while the
+// host still reads the previous batch's candidates
+struct DsoftBuf {
+    DsoftQuery *d_queries = nullptr, *h_queries = nullptr;
+    DsoftCand *d_out = nullptr;
+    gact_dsoft_cand *h_out = nullptr;                   // pinned
+    unsigned long long *d_count = nullptr, *h_count = nullptr;
+    int *d_counter = nullptr;
+    size_t q_cap = 0, out_cap = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr, ev_fork = nullptr;
+    int n_queries = 0;
+    size_t limit = 0;                                   // candidates the kernel may write / the copy brings back
+    bool busy = false;
+};
+constexpr int DSOFT_BUFS = 2;
+}  // namespace
+
 struct gact_dsoft {
     gact_engine *e = nullptr;
     DsoftParams p{};
     uint32_t *d_index = nullptr, *d_pos = nullptr;
     bool owns_tables = true;          // false: the tables belong to a gact_seed_table
     uint32_t *d_keys = nullptr, *d_touched = nullptr;
-    unsigned long long *d_vals = nullptr, *d_count = nullptr;
-    int *d_counter = nullptr;
-    DsoftQuery *d_queries = nullptr;
-    DsoftCand *d_out = nullptr;
-    size_t q_cap = 0, out_cap = 0;
+    unsigned long long *d_vals = nullptr;
+    cudaStream_t stream = nullptr;    // the filter's own stream: its kernels overlap the chain kernels of other batches
+    DsoftBuf buf[DSOFT_BUFS];
+    int head = 0, tail = 0, inflight = 0;
     int ctas = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = -1.0;
 };
+
+namespace {
+void free_dsoft_buf(DsoftBuf &b)
+{
+    cudaFree(b.d_queries); cudaFree(b.d_out); cudaFree(b.d_count); cudaFree(b.d_counter);
+    if (b.h_queries) cudaFreeHost(b.h_queries);
+    if (b.h_out) cudaFreeHost(b.h_out);
+    if (b.h_count) cudaFreeHost(b.h_count);
+    for (cudaEvent_t ev : {b.ev0, b.ev1, b.ev_done, b.ev_fork}) if (ev) cudaEventDestroy(ev);
+    b = DsoftBuf();
+}
+
+int reserve_dsoft_buf(gact_engine *e, DsoftBuf &b, size_t n_queries, size_t out_cap)
+{
+    if (!b.ev0) {
+        CU(e, cudaEventCreate(&b.ev0));
+        CU(e, cudaEventCreate(&b.ev1));
+        CU(e, cudaEventCreateWithFlags(&b.ev_done, cudaEventDisableTiming));
+        CU(e, cudaEventCreateWithFlags(&b.ev_fork, cudaEventDisableTiming));
+    }
+    if (!b.d_count) {
+        if (cudaMalloc(&b.d_count, 8) != cudaSuccess || cudaMalloc(&b.d_counter, 4) != cudaSuccess ||
+            cudaMallocHost(&b.h_count, 8) != cudaSuccess) { cudaGetLastError(); return fail(e, GACT_ERR_NOMEM, "cudaMalloc(D-SOFT counters) failed"); }
+    }
+    if (n_queries > b.q_cap) {
+        cudaFree(b.d_queries); if (b.h_queries) cudaFreeHost(b.h_queries);
+        b.d_queries = nullptr; b.h_queries = nullptr; b.q_cap = 0;
+        const size_t want = std::max<size_t>(n_queries, 64);
+        if (cudaMalloc(&b.d_queries, want * sizeof(DsoftQuery)) != cudaSuccess ||
+            cudaMallocHost(&b.h_queries, want * sizeof(DsoftQuery)) != cudaSuccess) { cudaGetLastError(); return fail(e, GACT_ERR_NOMEM, "cudaMalloc(queries) failed"); }
+        b.q_cap = want;
+    }
+    if (out_cap > b.out_cap || !b.d_out) {
+        cudaFree(b.d_out); if (b.h_out) cudaFreeHost(b.h_out);
+        b.d_out = nullptr; b.h_out = nullptr; b.out_cap = 0;
+        const size_t want = std::max<size_t>(out_cap, 1024);
+        if (cudaMalloc(&b.d_out, want * sizeof(DsoftCand)) != cudaSuccess ||
+            cudaMallocHost(&b.h_out, want * sizeof(gact_dsoft_cand)) != cudaSuccess) { cudaGetLastError(); return fail(e, GACT_ERR_NOMEM, "cudaMalloc(candidates) failed"); }
+        b.out_cap = want;
+    }
+    return GACT_OK;
+}
+}  // namespace
 
 extern "C" {
 
@@ -807,11 +866,11 @@ void gact_dsoft_destroy(gact_dsoft *d)
     if (!d) return;
     cudaSetDevice(d->e->device);
     cudaStreamSynchronize(d->e->stream);
+    if (d->stream) cudaStreamSynchronize(d->stream);
     if (d->owns_tables) { cudaFree(d->d_index); cudaFree(d->d_pos); }
     cudaFree(d->d_keys); cudaFree(d->d_touched); cudaFree(d->d_vals);
-    cudaFree(d->d_count); cudaFree(d->d_counter); cudaFree(d->d_queries); cudaFree(d->d_out);
-    if (d->ev0) cudaEventDestroy(d->ev0);
-    if (d->ev1) cudaEventDestroy(d->ev1);
+    for (int k = 0; k < DSOFT_BUFS; k++) free_dsoft_buf(d->buf[k]);
+    if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
 }
 
@@ -842,10 +901,9 @@ static int dsoft_alloc(gact_dsoft **out, gact_engine *e, int kmer_size, int wind
     bool ok = cudaMalloc(&d->d_keys, warps * cap * 4) == cudaSuccess &&
               cudaMalloc(&d->d_touched, warps * cap * 4) == cudaSuccess &&
               cudaMalloc(&d->d_vals, warps * cap * 8) == cudaSuccess &&
-              cudaMalloc(&d->d_count, 8) == cudaSuccess && cudaMalloc(&d->d_counter, 4) == cudaSuccess &&
-              cudaEventCreate(&d->ev0) == cudaSuccess && cudaEventCreate(&d->ev1) == cudaSuccess;
+              cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) == cudaSuccess;
     if (!ok) { cudaGetLastError(); gact_dsoft_destroy(d); return fail(e, GACT_ERR_NOMEM, "cudaMalloc(D-SOFT tables) failed"); }
-    cudaMemsetAsync(d->d_keys, 0, warps * cap * 4, e->stream);
+    cudaMemsetAsync(d->d_keys, 0, warps * cap * 4, d->stream);
     d->p.k = kmer_size; d->p.w = window_size; d->p.bin_size = bin_size; d->p.max_occ = kmer_max_occurence;
     d->p.num_seeds = num_seeds; d->p.threshold = threshold; d->p.max_candidates = max_candidates;
     d->p.table_cap = cap;
@@ -870,9 +928,9 @@ int gact_dsoft_create(gact_dsoft **out, gact_engine *e, const uint32_t *index_ta
         cudaGetLastError(); gact_dsoft_destroy(d);
         return fail(e, GACT_ERR_NOMEM, "cudaMalloc(D-SOFT tables) failed");
     }
-    cudaMemcpyAsync(d->d_index, index_table, index_entries * 4, cudaMemcpyHostToDevice, e->stream);
-    if (n_pos) cudaMemcpyAsync(d->d_pos, pos_table, n_pos * 4, cudaMemcpyHostToDevice, e->stream);
-    cudaError_t r = cudaStreamSynchronize(e->stream);
+    cudaMemcpyAsync(d->d_index, index_table, index_entries * 4, cudaMemcpyHostToDevice, d->stream);
+    if (n_pos) cudaMemcpyAsync(d->d_pos, pos_table, n_pos * 4, cudaMemcpyHostToDevice, d->stream);
+    cudaError_t r = cudaStreamSynchronize(d->stream);
     if (r != cudaSuccess) { gact_dsoft_destroy(d); return fail(e, GACT_ERR_CUDA, std::string("D-SOFT upload: ") + cudaGetErrorString(r)); }
     e->stats.h2d_bytes += (double)(index_entries + n_pos) * 4;
     d->p.index_table = d->d_index; d->p.pos_table = d->d_pos;
@@ -950,6 +1008,7 @@ int gact_dsoft_create_from_table(gact_dsoft **out, gact_engine *e, const gact_se
     d->d_index = t->t.d_index; d->d_pos = t->t.d_pos;      // borrowed: the table must outlive the filter
     d->p.index_table = d->d_index; d->p.pos_table = d->d_pos;
     CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, cudaStreamSynchronize(d->stream));
     *out = d;
     return GACT_OK;
 }
@@ -959,18 +1018,92 @@ int gact_dsoft_reserve(gact_dsoft *d, int n_queries, int64_t out_cap)
     if (!d || n_queries < 0 || out_cap < 0) return GACT_ERR_ARG;
     gact_engine *e = d->e;
     CU(e, cudaSetDevice(e->device));
-    if ((size_t)n_queries > d->q_cap) {
-        cudaFree(d->d_queries);
-        d->d_queries = nullptr;
-        if (cudaMalloc(&d->d_queries, (size_t)n_queries * sizeof(DsoftQuery)) != cudaSuccess) { cudaGetLastError(); d->q_cap = 0; return fail(e, GACT_ERR_NOMEM, "cudaMalloc(queries) failed"); }
-        d->q_cap = (size_t)n_queries;
+    for (int k = 0; k < DSOFT_BUFS; k++) {
+        if (d->buf[k].busy) continue;
+        int rc = reserve_dsoft_buf(e, d->buf[k], (size_t)n_queries, (size_t)out_cap);
+        if (rc) return rc;
     }
-    if ((size_t)out_cap > d->out_cap || !d->d_out) {
-        cudaFree(d->d_out);
-        d->d_out = nullptr;
-        const size_t want = std::max<size_t>((size_t)out_cap, 1024);
-        if (cudaMalloc(&d->d_out, want * sizeof(DsoftCand)) != cudaSuccess) { cudaGetLastError(); d->out_cap = 0; return fail(e, GACT_ERR_NOMEM, "cudaMalloc(candidates) failed"); }
-        d->out_cap = want;
+    return GACT_OK;
+}
+
+int gact_dsoft_submit(gact_dsoft *d, int n_queries, const int32_t *sets, const int64_t *seq_index, int64_t out_cap)
+{
+    if (!d || n_queries < 0 || (n_queries && (!sets || !seq_index)) || out_cap < 0) return GACT_ERR_ARG;
+    gact_engine *e = d->e;
+    if (d->inflight >= DSOFT_BUFS) return fail(e, GACT_ERR_STATE, "two D-SOFT batches already in flight");
+    CU(e, cudaSetDevice(e->device));
+    DsoftBuf &b = d->buf[d->head];
+    {
+        int rr = reserve_dsoft_buf(e, b, (size_t)n_queries, (size_t)out_cap);
+        if (rr) return rr;
+    }
+    for (int i = 0; i < n_queries; i++) {
+        const int s = sets[i];
+        if (s < 0 || s >= GACT_MAX_SETS) return fail(e, GACT_ERR_ARG, "bad set in D-SOFT query");
+        const SeqSetHost &hs = e->sets[s];
+        if (seq_index[i] < 0 || (size_t)seq_index[i] + 1 >= hs.starts.size()) return fail(e, GACT_ERR_ARG, "bad sequence index in D-SOFT query");
+        b.h_queries[i].start = hs.starts[(size_t)seq_index[i]];
+        b.h_queries[i].len = (int)(hs.starts[(size_t)seq_index[i] + 1] - hs.starts[(size_t)seq_index[i]]);
+        b.h_queries[i].set = s;
+    }
+    b.n_queries = n_queries;
+    b.limit = std::min<size_t>((size_t)out_cap, b.out_cap);
+    *b.h_count = 0;
+    cudaStream_t st = d->stream;
+    CU(e, cudaEventRecord(b.ev_fork, e->stream));          // ordered after uploads / table builds on the engine's stream
+    CU(e, cudaStreamWaitEvent(st, b.ev_fork, 0));
+    if (n_queries > 0) {
+        for (int i = 0; i < GACT_MAX_SETS; i++) d->p.sets[i] = e->kp.sets[i];
+        CU(e, cudaMemcpyAsync(b.d_queries, b.h_queries, (size_t)n_queries * sizeof(DsoftQuery), cudaMemcpyHostToDevice, st));
+        CU(e, cudaMemsetAsync(b.d_count, 0, 8, st));
+        CU(e, cudaMemsetAsync(b.d_counter, 0, 4, st));
+        CU(e, cudaEventRecord(b.ev0, st));
+        int ctas = d->ctas;
+        if ((n_queries + 3) / 4 < ctas) ctas = (n_queries + 3) / 4;
+        // the table area was sized for d->ctas CTAs of 4 warps; fewer CTAs use a prefix of it
+        dsoft_kernel<<<ctas, 128, 0, st>>>(d->p, b.d_queries, n_queries, d->d_keys, d->d_vals, d->d_touched,
+                                           b.d_out, (unsigned long long)b.limit, b.d_count, b.d_counter);
+        CU(e, cudaGetLastError());
+        CU(e, cudaEventRecord(b.ev1, st));
+        CU(e, cudaMemcpyAsync(b.h_count, b.d_count, 8, cudaMemcpyDeviceToHost, st));
+        // the count is not known to the host yet: bring back the whole window the kernel was allowed to fill
+        // (16 B per candidate, a few candidates per read)
+        if (b.limit) CU(e, cudaMemcpyAsync(b.h_out, b.d_out, b.limit * sizeof(DsoftCand), cudaMemcpyDeviceToHost, st));
+        e->stats.kernel_launches++;
+    }
+    CU(e, cudaEventRecord(b.ev_done, st));
+    b.busy = true;
+    d->head = (d->head + 1) % DSOFT_BUFS;
+    d->inflight++;
+    return GACT_OK;
+}
+
+int gact_dsoft_wait(gact_dsoft *d, gact_dsoft_cand *out, int64_t out_cap, int64_t *n_out)
+{
+    if (!d || !n_out || out_cap < 0 || (out_cap && !out)) return GACT_ERR_ARG;
+    gact_engine *e = d->e;
+    *n_out = 0;
+    if (d->inflight == 0) return fail(e, GACT_ERR_STATE, "dsoft_wait without dsoft_submit");
+    CU(e, cudaSetDevice(e->device));
+    DsoftBuf &b = d->buf[d->tail];
+    CU(e, cudaEventSynchronize(b.ev_done));
+    b.busy = false;
+    d->tail = (d->tail + 1) % DSOFT_BUFS;
+    d->inflight--;
+    if (b.n_queries == 0) return GACT_OK;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, b.ev0, b.ev1);
+    d->last_ms = ms;
+    const unsigned long long total = *b.h_count;
+    *n_out = (int64_t)total;
+    if (total > b.limit || (int64_t)total > out_cap) return fail(e, GACT_ERR_NOMEM, "candidate buffer too small (see *n_out)");
+    if (total) {
+        static_assert(sizeof(DsoftCand) == sizeof(gact_dsoft_cand), "candidate layouts differ");
+        memcpy(out, b.h_out, (size_t)total * sizeof(gact_dsoft_cand));
+        std::sort(out, out + total, [](const gact_dsoft_cand &a, const gact_dsoft_cand &c) {
+            return a.query != c.query ? a.query < c.query : a.seq < c.seq;
+        });
+        e->stats.d2h_bytes += (double)total * sizeof(DsoftCand);
     }
     return GACT_OK;
 }
@@ -980,55 +1113,12 @@ int gact_dsoft_run(gact_dsoft *d, int n_queries, const int32_t *sets, const int6
 {
     if (!d || n_queries < 0 || (n_queries && (!sets || !seq_index)) || !n_out || out_cap < 0 || (out_cap && !out))
         return GACT_ERR_ARG;
-    gact_engine *e = d->e;
     *n_out = 0;
+    if (d->inflight) return fail(d->e, GACT_ERR_STATE, "dsoft_run while asynchronous D-SOFT batches are in flight");
     if (n_queries == 0) return GACT_OK;
-    CU(e, cudaSetDevice(e->device));
-    std::vector<DsoftQuery> q((size_t)n_queries);
-    for (int i = 0; i < n_queries; i++) {
-        const int s = sets[i];
-        if (s < 0 || s >= GACT_MAX_SETS) return fail(e, GACT_ERR_ARG, "bad set in D-SOFT query");
-        const SeqSetHost &hs = e->sets[s];
-        if (seq_index[i] < 0 || (size_t)seq_index[i] + 1 >= hs.starts.size()) return fail(e, GACT_ERR_ARG, "bad sequence index in D-SOFT query");
-        q[(size_t)i].start = hs.starts[(size_t)seq_index[i]];
-        q[(size_t)i].len = (int)(hs.starts[(size_t)seq_index[i] + 1] - hs.starts[(size_t)seq_index[i]]);
-        q[(size_t)i].set = s;
-    }
-    {
-        int rr = gact_dsoft_reserve(d, n_queries, out_cap);
-        if (rr) return rr;
-    }
-    for (int i = 0; i < GACT_MAX_SETS; i++) d->p.sets[i] = e->kp.sets[i];
-    cudaStream_t st = e->stream;
-    CU(e, cudaMemcpyAsync(d->d_queries, q.data(), (size_t)n_queries * sizeof(DsoftQuery), cudaMemcpyHostToDevice, st));
-    CU(e, cudaMemsetAsync(d->d_count, 0, 8, st));
-    CU(e, cudaMemsetAsync(d->d_counter, 0, 4, st));
-    CU(e, cudaEventRecord(d->ev0, st));
-    int ctas = d->ctas;
-    if ((n_queries + 3) / 4 < ctas) ctas = (n_queries + 3) / 4;
-    // the table area was sized for d->ctas CTAs of 4 warps; fewer CTAs use a prefix of it
-    dsoft_kernel<<<ctas, 128, 0, st>>>(d->p, d->d_queries, n_queries, d->d_keys, d->d_vals, d->d_touched,
-                                       d->d_out, (unsigned long long)std::min<size_t>((size_t)out_cap, d->out_cap), d->d_count, d->d_counter);
-    CU(e, cudaGetLastError());
-    CU(e, cudaEventRecord(d->ev1, st));
-    unsigned long long total = 0;
-    CU(e, cudaMemcpyAsync(&total, d->d_count, 8, cudaMemcpyDeviceToHost, st));
-    CU(e, cudaStreamSynchronize(st));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, d->ev0, d->ev1);
-    d->last_ms = ms;
-    e->stats.kernel_launches++;
-    *n_out = (int64_t)total;
-    if ((int64_t)total > out_cap) return fail(e, GACT_ERR_NOMEM, "candidate buffer too small (see *n_out)");
-    if (total) {
-        static_assert(sizeof(DsoftCand) == sizeof(gact_dsoft_cand), "candidate layouts differ");
-        CU(e, cudaMemcpy(out, d->d_out, (size_t)total * sizeof(DsoftCand), cudaMemcpyDeviceToHost));
-        std::sort(out, out + total, [](const gact_dsoft_cand &a, const gact_dsoft_cand &b) {
-            return a.query != b.query ? a.query < b.query : a.seq < b.seq;
-        });
-        e->stats.d2h_bytes += (double)total * sizeof(DsoftCand);
-    }
-    return GACT_OK;
+    int rc = gact_dsoft_submit(d, n_queries, sets, seq_index, out_cap);
+    if (rc) return rc;
+    return gact_dsoft_wait(d, out, out_cap, n_out);
 }
 
 double gact_dsoft_last_kernel_ms(const gact_dsoft *d) { return d ? d->last_ms : -1.0; }

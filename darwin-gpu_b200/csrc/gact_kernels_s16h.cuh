@@ -7,6 +7,7 @@
 // and spreads the per-step overhead (edge shuffle, predicates, row fetch) over twice as many
 // cells.  The direction window lives in per-segment global scratch (L2-resident).
 #pragma once
+#include <type_traits>
 #include "gact_kernels_s16.cuh"
 
 namespace gact {
@@ -16,9 +17,13 @@ struct DirWinH {
     static constexpr int NW = CS / 4;                 // 32-bit words per lane-step (4 columns x 2 strips each)
     static constexpr int R = CS % 4;                  // leftover columns, kept in one 16-bit field (R <= 2)
     static_assert(R <= 2, "unsupported strip width");
+    // leftover columns of a lane-step (both strips): one byte for R = 1 (4 bits per strip), two for R = 2
+    struct HT1 { typedef uint8_t type; };
+    struct HT2 { typedef uint16_t type; };
+    typedef typename std::conditional<R == 1, HT1, HT2>::type::type HT;
     int i0, lane0, nl;
     uint32_t *w;
-    uint16_t *h;
+    HT *h;
     __device__ __forceinline__ void init(void *base, int n, int m, const KParams &P)
     {
         i0 = max(n - P.et, 1);
@@ -26,7 +31,13 @@ struct DirWinH {
         lane0 = ((j0 - 1) / CS) >> 1;
         nl = P.win_lanes;
         w = reinterpret_cast<uint32_t *>(base);
-        h = reinterpret_cast<uint16_t *>(w + (size_t)(P.win_rows + 1) * nl * NW);
+        h = reinterpret_cast<HT *>(w + (size_t)(P.win_rows + 1) * nl * NW);
+    }
+    // the leftover field of a lane-step from the accumulator word (low strip's codes in bits 7:0, high strip's in 23:16)
+    static __device__ __forceinline__ HT pack_rest(uint32_t acc)
+    {
+        if (R == 1) return (HT)((acc & 0xfu) | ((acc >> 12) & 0xf0u));
+        return (HT)((acc & 0xffu) | ((acc >> 8) & 0xff00u));
     }
     // 4-bit code of cell (i, j): bits 3:2 = M/I/D tag, bit 1 = ins flag, bit 0 = del flag
     __device__ __forceinline__ int load(int i, int j) const
@@ -35,11 +46,12 @@ struct DirWinH {
         const int lane = s >> 1, half = s & 1;
         const int e = (i + half - i0) * nl + (lane - lane0);
         if (c < NW * 4) return (w[e * NW + (c >> 2)] >> (16 * half + 4 * (3 - (c & 3)))) & 15;
+        if (R == 1) return (h[e] >> (4 * half)) & 15;
         return (h[e] >> (8 * half + 4 * (R - 1 - (c - NW * 4)))) & 15;
     }
     static __host__ __device__ size_t bytes(int win_rows, int win_lanes)
     {
-        size_t s = (size_t)(win_rows + 1) * win_lanes * (NW * 4 + (R ? 2 : 0));
+        size_t s = (size_t)(win_rows + 1) * win_lanes * (NW * 4 + R);
         return (s + 15) & ~(size_t)15;
     }
 };
@@ -268,7 +280,7 @@ __device__ __forceinline__ int seg_dp(const SegCtx<CS, LANES> &cx, const uint32_
 
     // ---------------- phase 2: window rows, tagged values + direction codes ----------------
     uint32_t *wptr = dw.w + ((k - 2 * sl - dw.i0) * dw.nl + (sl - dw.lane0)) * NW;
-    uint16_t *hptr = dw.h + ((k - 2 * sl - dw.i0) * dw.nl + (sl - dw.lane0));
+    typename DirWinH<CS>::HT *hptr = dw.h + ((k - 2 * sl - dw.i0) * dw.nl + (sl - dw.lane0));
     int corner16 = B;
     // the loop stops at the corner step of each segment (at most two different ones per warp) so that the corner
     // value is picked out of the registers outside the loop
@@ -303,7 +315,7 @@ __device__ __forceinline__ int seg_dp(const SegCtx<CS, LANES> &cx, const uint32_
         if (k >= kstore && k <= kend) {
 #pragma unroll
             for (int x = 0; x < NW; x++) wptr[x] = acc[x];
-            if (R) *hptr = (uint16_t)((acc[NW] & 0xffu) | ((acc[NW] >> 8) & 0xff00u));
+            if (R) *hptr = DirWinH<CS>::pack_rest(acc[NW]);
         }
         wptr += dw.nl * NW;
         hptr += dw.nl;
@@ -512,7 +524,7 @@ gact_tile_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *_
         DirWinH<CS> dw;
         dw.init(cx.dirbase, n, m, P);
         const int corner = seg_dp<CS, LANES, LUT>(cx, q, n, m, dw);
-        uint8_t *stbuf = reinterpret_cast<uint8_t *>(cx.rr);      // rr[] is dead after the DP
+        uint8_t *stbuf = reinterpret_cast<uint8_t *>(cx.rr + 1);  // rows >= 1 of rr[] are dead after the DP (rr[<= 0] must stay sentinel)
         const SegTrace tr = seg_traceback<CS, LANES, true>(cx, dw, n, m, corner, stbuf, 0);
         if (valid) {
             uint32_t *out = states + (size_t)t * pitch_words;

@@ -14,6 +14,10 @@
 //                        engine supports it; 0: tile-by-tile host scheduler (GactScheduler)
 //   DARWIN_DSOFT=<gpu|host> where the D-SOFT filter runs (default gpu: gact_dsoft_run on the shard's GPU;
 //                        host: SeedTable::dsoft on CPU_THREADS / n host threads)
+//   DARWIN_BATCH_READS=<n> reads per pipeline batch of a shard (default: auto, about 1 200; 0 = one batch): D-SOFT of
+//                        batch k+1 and the output of batch k-1 overlap the alignment chains of batch k
+//   DARWIN_SORTED_OUT=<file> additionally write the sorted, duplicate-free union of all darwin.<tid>.out lines
+//                        (what README:32 builds with `cat darwin.*.out | sort | uniq`)
 //
 // Flow per GPU shard: D-SOFT on the host for every read of the shard (CPU_THREADS / n
 // threads), then all candidates of the shard go through GactScheduler, then the overlap
@@ -48,6 +52,10 @@ static long ms_since(Clock::time_point t0)
 {
     return (long)(std::chrono::duration<double, std::milli>(Clock::now() - t0).count() + 0.5);
 }
+static double us_since(Clock::time_point t0)
+{
+    return std::chrono::duration<double, std::micro>(Clock::now() - t0).count();
+}
 
 static std::mutex io_lock;
 
@@ -57,6 +65,10 @@ struct Shard {
     int dsoft_threads = 1;
     SchedulerStats stats;
     long dsoft_ms = 0, gact_ms = 0, init_ms = 0;
+    double setup_us = 0;                       // worker start: thread creation, device binding, output file creation
+    double dsoft_wait_us = 0, extend_wait_us = 0, write_us = 0;   // pipelined path: host time blocked on the device / writing
+    int batches = 0;
+    std::vector<std::string> text;             // output of the shard, one string per batch (for DARWIN_SORTED_OUT)
     uint64_t cand_fwd = 0, cand_rev = 0;
     std::string error;
     gact_engine *eng = nullptr;               // created before the align phase (like GPU_init, darwin.cpp:611)
@@ -275,6 +287,146 @@ int main(int argc, char **argv)
 
     std::cout << "\nFinding candidate bin locations for each read: " << std::endl;
 
+    // Pipelined shard (GPU D-SOFT + on-device chains).  The D-SOFT filter runs once for the whole shard (half a millisecond of
+    // kernel time for 50 MB of reads); the candidates then go through gact_engine_extend_submit / _wait in batches of
+    // consecutive reads, up to GACT_MAX_INFLIGHT batches on their own streams, and a writer thread formats and writes
+    // batch k while the chains of the following batches run.
+    size_t batch_reads_env = 0;
+    bool batch_reads_set = false;
+    if (const char *b = getenv("DARWIN_BATCH_READS")) { batch_reads_env = (size_t)std::max(0, atoi(b)); batch_reads_set = true; }
+    auto run_shard_pipelined = [&](Shard &sh, std::ofstream &fout) {
+        try {
+            const size_t nr = sh.last_read - sh.first_read;
+            if (!fout.is_open()) { sh.error = "ERROR cannot open output file"; return; }
+            const auto td = Clock::now();
+            gact_engine *eng = sh.eng;
+
+            // ---- D-SOFT: queries = (reads, k), (reverse-complemented reads, k) for every read of the shard ----
+            std::vector<int32_t> qsets(2 * nr);
+            std::vector<int64_t> qidx(2 * nr);
+            for (size_t k = 0; k < nr; k++) {
+                qsets[2 * k] = GACT_SET_READS; qsets[2 * k + 1] = GACT_SET_READS_RC;
+                qidx[2 * k] = qidx[2 * k + 1] = (int64_t)k;
+            }
+            std::vector<gact_dsoft_cand> cands(std::max<size_t>(1024, 8 * nr));
+            int64_t n_cands = 0;
+            int rc = gact_dsoft_run(sh.dsoft, (int)(2 * nr), qsets.data(), qidx.data(), cands.data(), (int64_t)cands.size(), &n_cands);
+            if (rc == GACT_ERR_NOMEM && n_cands > (int64_t)cands.size()) {
+                cands.resize((size_t)n_cands);
+                rc = gact_dsoft_run(sh.dsoft, (int)(2 * nr), qsets.data(), qidx.data(), cands.data(), (int64_t)cands.size(), &n_cands);
+            }
+            if (rc) { sh.error = std::string("gact_dsoft_run: ") + gact_last_error(eng); return; }
+            sh.dsoft_wait_us = us_since(td);
+
+            // ---- batches of consecutive reads ----
+            size_t per_batch = nr;
+            if (batch_reads_set) per_batch = batch_reads_env ? batch_reads_env : nr;
+            else if (nr > 1800) { const size_t nb = (nr + 1199) / 1200; per_batch = (nr + nb - 1) / nb; }
+            per_batch = std::max<size_t>(per_batch, 1);
+            const size_t B = std::max<size_t>(1, (nr + per_batch - 1) / per_batch);
+            sh.batches = (int)B;
+            struct Batch { std::vector<GactCall> calls; std::vector<gact_call> gc; std::vector<gact_alignment> ga; };
+            std::vector<Batch> bt(B);
+            // candidates arrive grouped by query (= read, strand) in emission order, i.e. in the reference CPU build's
+            // order per read: forward candidates, then reverse (darwin.cpp:209-288)
+            for (int64_t i = 0; i < n_cands; i++) {
+                const gact_dsoft_cand &c = cands[(size_t)i];
+                const bool comp = (c.query & 1) != 0;
+                const size_t local = (size_t)(c.query >> 1);                              // read index inside the shard
+                int ref_pos = (int)c.hit;
+                const int chr = bin_to_chr[(uint32_t)ref_pos / cfg.bin_size];
+                ref_pos -= (int)(chr_start_bin[chr] * cfg.bin_size);
+                if (ref_pos > (long long)ref.seqs[chr].size()) ref_pos = (int)ref.seqs[chr].size();       // darwin.cpp:222-224
+                (comp ? sh.cand_rev : sh.cand_fwd)++;
+                Batch &x = bt[std::min(B - 1, local / per_batch)];
+                x.calls.push_back(GactCall{chr, (int32_t)local, ref_pos, (int)c.offset, (uint8_t)(comp ? 1 : 0)});
+                gact_call g;
+                memset(&g, 0, sizeof(g));
+                g.ref_seq = chr; g.query_seq = (int32_t)local; g.ref_pos = ref_pos; g.query_pos = (int)c.offset;
+                g.query_set = comp ? GACT_SET_READS_RC : GACT_SET_READS;
+                x.gc.push_back(g);
+            }
+            for (Batch &x : bt) x.ga.resize(x.gc.size());
+            sh.text.assign(B, std::string());
+            sh.dsoft_ms = ms_since(td);
+            {
+                std::lock_guard<std::mutex> lk(io_lock);
+                printf("num_candidates: %llu %llu\n", (unsigned long long)sh.cand_fwd, (unsigned long long)sh.cand_rev);
+                std::cout << "Time finding seeds: " << sh.dsoft_ms << " msec" << std::endl;
+            }
+            const auto tg = Clock::now();
+
+            // writer thread: batches in order, same line order as the sequential loop of the reference
+            std::mutex wm;
+            std::condition_variable wcv;
+            size_t ready = 0;                         // batches whose alignments are complete
+            bool stop_writer = false;
+            std::thread writer([&] {
+                for (size_t b = 0; b < B; b++) {
+                    {
+                        std::unique_lock<std::mutex> lk(wm);
+                        wcv.wait(lk, [&] { return ready > b || stop_writer; });
+                        if (ready <= b) return;       // aborted
+                    }
+                    const auto tw = Clock::now();
+                    const Batch &x = bt[b];
+                    std::string &out = sh.text[b];
+                    out.reserve(x.calls.size() * 112);
+                    for (size_t k = 0; k < x.calls.size(); k++) {
+                        const GactCall &c = x.calls[k];
+                        const size_t read_id = sh.first_read + (size_t)c.query_id;
+                        const gact_alignment &a = x.ga[k];
+                        if (!(same_file && (size_t)c.ref_id == read_id) && a.score > 0)        // gact.cpp:213
+                            out += format_overlap(ref.names[c.ref_id], reads.names[read_id],
+                                                  GactAlignment{a.ab, a.ae, a.bb, a.be, a.score, a.first_tile_score, a.n_tiles, a.n_cells},
+                                                  c.complement != 0);
+                    }
+                    fout.write(out.data(), (std::streamsize)out.size());
+                    sh.write_us += us_since(tw);
+                }
+                fout.close();
+            });
+            auto finish_writer = [&](bool abort) {
+                { std::lock_guard<std::mutex> lk(wm); if (abort) stop_writer = true; }
+                wcv.notify_all();
+                if (writer.joinable()) writer.join();
+            };
+            auto extend_collect = [&](size_t b) -> int {
+                const auto tw = Clock::now();
+                const int r = gact_engine_extend_wait(eng, bt[b].ga.data());
+                sh.extend_wait_us += us_since(tw);
+                if (r) return r;
+                for (const gact_alignment &a : bt[b].ga) { sh.stats.tiles += (uint64_t)a.n_tiles; sh.stats.cells += (uint64_t)a.n_cells; }
+                { std::lock_guard<std::mutex> lk(wm); ready = b + 1; }
+                wcv.notify_all();
+                return GACT_OK;
+            };
+            size_t collected = 0;
+            rc = GACT_OK;
+            for (size_t b = 0; b < B && !rc; b++) {
+                while (!rc && b - collected >= (size_t)GACT_MAX_INFLIGHT) rc = extend_collect(collected++);
+                if (!rc) rc = gact_engine_extend_submit(eng, (int)bt[b].gc.size(), bt[b].gc.data());
+            }
+            while (!rc && collected < B) rc = extend_collect(collected++);
+            if (rc) { finish_writer(true); sh.error = std::string("gact_engine_extend: ") + gact_last_error(eng); return; }
+            finish_writer(false);
+            gact_stats es;
+            gact_engine_stats(eng, &es);
+            sh.stats.device_ms = es.kernel_ms;
+            sh.stats.rounds = B;
+            sh.gact_ms = ms_since(tg);
+            sh.stats.wall_ms = (double)sh.gact_ms;
+            {
+                std::lock_guard<std::mutex> lk(io_lock);
+                std::cout << "Time GACT calling: " << sh.gact_ms << " msec (" << B << " batch(es) of chains; host blocked on chains "
+                          << (long)(sh.extend_wait_us / 1e3 + 0.5) << " msec; writer thread busy " << (long)(sh.write_us / 1e3 + 0.5)
+                          << " msec)" << std::endl;
+            }
+        } catch (const std::exception &e) {
+            sh.error = e.what();
+        }
+    };
+
     auto run_shard = [&](Shard &sh, std::ofstream &fout) {
         try {
             const size_t nr = sh.last_read - sh.first_read;
@@ -440,18 +592,21 @@ int main(int argc, char **argv)
     bool go = false;
     for (auto &sh : shards) {
         Shard *shp = &sh;
-        workers.emplace_back([&, shp] {
+        const auto t_spawn = Clock::now();
+        workers.emplace_back([&, shp, t_spawn] {
             gact_engine_sync(shp->eng);
             // output file of this worker (darwin.cpp:203-204), created before the bracket: the first file creation of the
             // process was measured at 12-40 ms on the test boxes' file system, next to a 10 ms alignment phase
             std::ofstream fout("darwin." + std::to_string(shp->tid) + ".out");
+            shp->setup_us = us_since(t_spawn);
             {
                 std::unique_lock<std::mutex> lk(gate_m);
                 parked++;
                 gate_cv.notify_all();
                 gate_cv.wait(lk, [&] { return go; });
             }
-            run_shard(*shp, fout);
+            if (shp->dsoft && use_chains && gact_engine_extend_supported(shp->eng)) run_shard_pipelined(*shp, fout);
+            else run_shard(*shp, fout);
             {
                 std::lock_guard<std::mutex> lk(gate_m);
                 finished++;
@@ -469,12 +624,14 @@ int main(int argc, char **argv)
     std::cout << workers.size() << " threads created\n";
     std::cout << "Synchronizing all threads...\n";
     long align_ms = 0;
+    double align_us = 0;
     {
         // the bracket closes when every shard has written its output; the threads' exit (the CUDA runtime's
         // per-thread teardown) is joined afterwards, next to GPU_close
         std::unique_lock<std::mutex> lk(gate_m);
         gate_cv.wait(lk, [&] { return finished == shards.size(); });
-        align_ms = ms_since(t0);
+        align_us = us_since(t0);
+        align_ms = (long)(align_us / 1e3 + 0.5);
     }
     const auto t_join = Clock::now();
     for (auto &w : workers) w.join();

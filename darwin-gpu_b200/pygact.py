@@ -56,7 +56,7 @@ EXPORTS = [
     "gact_engine_set_kernel", "gact_engine_get_kernel", "gact_int_peak",
     "gact_engine_extend", "gact_engine_extend_supported", "gact_engine_extend_reserve", "gact_dsoft_reserve",
     "gact_engine_extend_submit", "gact_engine_extend_wait", "gact_engine_set_chain_mode", "gact_engine_chain_info",
-    "gact_dsoft_create", "gact_dsoft_destroy", "gact_dsoft_run", "gact_dsoft_last_kernel_ms",
+    "gact_dsoft_create", "gact_dsoft_destroy", "gact_dsoft_run", "gact_dsoft_last_kernel_ms", "gact_dsoft_submit", "gact_dsoft_wait",
     "gact_seed_table_build", "gact_seed_table_destroy", "gact_seed_table_info", "gact_seed_table_download",
     "gact_dsoft_create_from_table",
 ]
@@ -147,6 +147,10 @@ def load():
     L.gact_dsoft_destroy.argtypes = [vp]
     L.gact_dsoft_run.restype = i32
     L.gact_dsoft_run.argtypes = [vp, i32, vp, vp, vp, i64, C.POINTER(i64)]
+    L.gact_dsoft_submit.restype = i32
+    L.gact_dsoft_submit.argtypes = [vp, i32, vp, vp, i64]
+    L.gact_dsoft_wait.restype = i32
+    L.gact_dsoft_wait.argtypes = [vp, vp, i64, C.POINTER(i64)]
     L.gact_dsoft_last_kernel_ms.restype = C.c_double
     L.gact_dsoft_last_kernel_ms.argtypes = [vp]
     L.gact_seed_table_build.restype = i32
@@ -422,6 +426,19 @@ class Dsoft:
                 continue
             self.eng._ck(rc, "gact_dsoft_run")
             return out[:n.value]
+
+    def submit(self, sets, seq_index, cap=1 << 16):
+        sets = np.ascontiguousarray(sets, dtype=np.int32)
+        seq_index = np.ascontiguousarray(seq_index, dtype=np.int64)
+        self.eng._ck(self.eng.L.gact_dsoft_submit(self.h, len(sets), sets.ctypes.data, seq_index.ctypes.data, cap), "gact_dsoft_submit")
+        self._caps = getattr(self, "_caps", []) + [cap]
+
+    def wait(self):
+        cap = self._caps.pop(0)
+        out = np.zeros(cap, dtype=DSOFT_CAND_DTYPE)
+        n = C.c_int64(0)
+        self.eng._ck(self.eng.L.gact_dsoft_wait(self.h, out.ctypes.data, cap, C.byref(n)), "gact_dsoft_wait")
+        return out[:n.value]
 
     def last_kernel_ms(self):
         return self.eng.L.gact_dsoft_last_kernel_ms(self.h)

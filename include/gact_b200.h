@@ -289,6 +289,10 @@ int  gact_dsoft_create_from_table(gact_dsoft **out, gact_engine *e, const gact_s
  * required capacity when out_cap is too small. */
 int  gact_dsoft_run(gact_dsoft *d, int n_queries, const int32_t *sets, const int64_t *seq_index,
                     gact_dsoft_cand *out, int64_t out_cap, int64_t *n_out);
+/* Asynchronous form on the filter's own stream (two batches in flight at most): submit enqueues the queries, the
+ * kernel and the copy of up to out_cap candidates; wait returns the oldest batch's candidates like gact_dsoft_run. */
+int  gact_dsoft_submit(gact_dsoft *d, int n_queries, const int32_t *sets, const int64_t *seq_index, int64_t out_cap);
+int  gact_dsoft_wait(gact_dsoft *d, gact_dsoft_cand *out, int64_t out_cap, int64_t *n_out);
 double gact_dsoft_last_kernel_ms(const gact_dsoft *d);
 /* Optional: allocate the device buffers for n_queries queries / out_cap candidates now. */
 int  gact_dsoft_reserve(gact_dsoft *d, int n_queries, int64_t out_cap);

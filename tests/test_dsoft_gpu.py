@@ -47,6 +47,15 @@ def run_case(G, H, refs, reads, k=14, w=4, bin_size=64, num_seeds=800, threshold
             idx += [i, i]
         got = ds.run(sets, idx, cap=64)                 # small capacity: exercises the grow-and-retry path
         ms = ds.last_kernel_ms()
+        # asynchronous form: two batches in flight (halves of the query list), same candidates
+        half = (len(sets) // 4) * 2
+        ds.submit(sets[:half], idx[:half], cap=max(64, len(got)))
+        ds.submit(sets[half:], idx[half:], cap=max(64, len(got)))
+        a, b = ds.wait(), ds.wait()
+        b = b.copy()
+        b["query"] += half
+        both = np.concatenate([a, b])
+        assert len(both) == len(got) and (both == got).all()
         ds.close()
     # host implementation (pinned to the reference by tests/test_host.py)
     n_q = len(sets)
