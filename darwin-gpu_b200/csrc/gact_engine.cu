@@ -78,6 +78,7 @@ struct gact_engine {
     Slot slots[GACT_MAX_INFLIGHT];
     int head = 0, tail = 0, inflight = 0;   // async ring
     bool staged = false;
+    bool slots_ready = false;
     double last_kernel_ms = -1.0;
     struct gact_chain_state *chains = nullptr;       // gact_engine_extend_* state (created on first use)
     gact_stats stats{};
@@ -369,6 +370,36 @@ int finish(gact_engine *e, Slot &s, gact_tile_result *results, uint32_t *packed_
     return GACT_OK;
 }
 
+// The batch slots of the tile path (device + pinned host copies of descriptors, results, states) are allocated at the first
+// tile batch: a caller that only extends whole candidates on the device (gact_engine_extend) never pays for them.
+int ensure_slots(gact_engine *e)
+{
+    if (e->slots_ready) return GACT_OK;
+    for (int k = 0; k < GACT_MAX_INFLIGHT; k++) {
+        Slot &s = e->slots[k];
+        const size_t n = (size_t)e->max_tiles;
+        CU(e, cudaMalloc(&s.d_descs, n * sizeof(gact_tile_desc)));
+        CU(e, cudaMalloc(&s.d_results, n * sizeof(gact_tile_result)));
+        CU(e, cudaMalloc(&s.d_states, n * e->pitch_words * 4));
+        CU(e, cudaMalloc(&s.d_eff, n * sizeof(EffLen)));
+        CU(e, cudaMalloc(&s.d_first, n * sizeof(int)));
+        CU(e, cudaMalloc(&s.d_order, n * sizeof(int)));
+        CU(e, cudaMallocHost(&s.h_order, n * sizeof(int)));
+        CU(e, cudaMalloc(&s.d_counters, 2 * sizeof(int)));
+        CU(e, cudaMallocHost(&s.h_descs, n * sizeof(gact_tile_desc)));
+        CU(e, cudaMallocHost(&s.h_results, n * sizeof(gact_tile_result)));
+        CU(e, cudaMallocHost(&s.h_states, n * e->pitch_words * 4));
+        CU(e, cudaMallocHost(&s.h_first, n * sizeof(int)));
+        CU(e, cudaEventCreate(&s.ev_k0));
+        CU(e, cudaEventCreate(&s.ev_k1));
+        CU(e, cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+        CU(e, cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+        CU(e, cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+    }
+    e->slots_ready = true;
+    return GACT_OK;
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -453,27 +484,6 @@ int gact_engine_create(gact_engine **out, int device, const gact_params *p, int 
         rc = plan_launch(e);
         if (rc) { g_create_error = e->err; goto bad; }
 
-        for (int k = 0; k < GACT_MAX_INFLIGHT; k++) {
-            Slot &s = e->slots[k];
-            const size_t n = (size_t)max_tiles;
-            CK(cudaMalloc(&s.d_descs, n * sizeof(gact_tile_desc)));
-            CK(cudaMalloc(&s.d_results, n * sizeof(gact_tile_result)));
-            CK(cudaMalloc(&s.d_states, n * e->pitch_words * 4));
-            CK(cudaMalloc(&s.d_eff, n * sizeof(EffLen)));
-            CK(cudaMalloc(&s.d_first, n * sizeof(int)));
-            CK(cudaMalloc(&s.d_order, n * sizeof(int)));
-            CK(cudaMallocHost(&s.h_order, n * sizeof(int)));
-            CK(cudaMalloc(&s.d_counters, 2 * sizeof(int)));
-            CK(cudaMallocHost(&s.h_descs, n * sizeof(gact_tile_desc)));
-            CK(cudaMallocHost(&s.h_results, n * sizeof(gact_tile_result)));
-            CK(cudaMallocHost(&s.h_states, n * e->pitch_words * 4));
-            CK(cudaMallocHost(&s.h_first, n * sizeof(int)));
-            CK(cudaEventCreate(&s.ev_k0));
-            CK(cudaEventCreate(&s.ev_k1));
-            CK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
-        }
     }
 #undef CK
     *out = e;
@@ -606,6 +616,7 @@ int gact_engine_max_tiles(const gact_engine *e) { return e ? e->max_tiles : -1; 
 int gact_engine_submit(gact_engine *e, int n, const gact_tile_desc *descs)
 {
     if (!e) return GACT_ERR_ARG;
+    { CU(e, cudaSetDevice(e->device)); int rs = ensure_slots(e); if (rs) return rs; }
     if (e->staged) return fail(e, GACT_ERR_STATE, "submit while a staged batch is pending");
     if (e->inflight >= GACT_MAX_INFLIGHT) return fail(e, GACT_ERR_STATE, "GACT_MAX_INFLIGHT batches already in flight");
     CU(e, cudaSetDevice(e->device));
@@ -665,6 +676,7 @@ int gact_engine_align_tiles(gact_engine *e, int n, const gact_tile_desc *descs,
                             gact_tile_result *results, uint32_t *packed_states)
 {
     if (!e) return GACT_ERR_ARG;
+    { CU(e, cudaSetDevice(e->device)); int rs = ensure_slots(e); if (rs) return rs; }
     if (e->inflight) return fail(e, GACT_ERR_STATE, "align_tiles while async batches are in flight");
     if (e->staged) return fail(e, GACT_ERR_STATE, "align_tiles while a staged batch is pending");
     CU(e, cudaSetDevice(e->device));
@@ -684,6 +696,7 @@ int gact_engine_align_tiles(gact_engine *e, int n, const gact_tile_desc *descs,
 int gact_engine_stage(gact_engine *e, int n, const gact_tile_desc *descs)
 {
     if (!e) return GACT_ERR_ARG;
+    { CU(e, cudaSetDevice(e->device)); int rs = ensure_slots(e); if (rs) return rs; }
     if (e->inflight) return fail(e, GACT_ERR_STATE, "stage while async batches are in flight");
     CU(e, cudaSetDevice(e->device));
     Slot &s = e->slots[0];
@@ -751,6 +764,13 @@ int gact_engine_fetch_staged(gact_engine *e, gact_tile_result *results, uint32_t
     }
     e->staged = false;
     return GACT_OK;
+}
+
+int gact_engine_reserve_tiles(gact_engine *e)
+{
+    if (!e) return GACT_ERR_ARG;
+    CU(e, cudaSetDevice(e->device));
+    return ensure_slots(e);
 }
 
 int gact_engine_stats(const gact_engine *e, gact_stats *out)
@@ -1325,16 +1345,20 @@ int gact_engine_extend_submit(gact_engine *e, int n, const gact_call *calls)
         const double per_sub = 0.5 * est_sum / (4.0 * e->num_sms);
         const double thr_slots = (double)e->s16h.slots();
         if (mode == 0) {
+            // measured on B200 (profiles/r2_chain_modes.txt; 1/8, 1/4, 1/2 and the whole of a 50 MB read set):
+            // load per sub-partition below 0.6 longest chains -> every long chain alone on a sub-partition;
+            // up to 2 longest chains -> the 4 * SMs longest chains on the latency kernel beside the throughput kernel; above
+            // that the shard is work-bound and the throughput kernel alone is fastest
             if (!lat_ok) mode = 3;
-            else if (per_sub <= 0.7 * est_max) mode = 1;
-            else if (per_sub <= 1.4 * est_max) mode = 2;
-            else mode = (n > thr_slots) ? 4 : 3;
+            else if (per_sub <= 0.6 * est_max) mode = 1;
+            else if (per_sub <= 2.0 * est_max) mode = 4;
+            else mode = 3;
         }
         if (!lat_ok && mode != 3) mode = 3;
         int n_long = 0;
         if (mode == 4) {
-            // chains whose serial length exceeds 60 % of the average load per chain slot of the throughput kernel,
-            // at most one per sub-partition
+            // the longest chains, one per SM sub-partition at most, as long as their serial length exceeds 60 % of the
+            // average load per chain slot of the throughput kernel
             const double long_tiles = 0.6 * est_sum / thr_slots;
             const int cap_long = 4 * e->num_sms;
             while (n_long < n && n_long < cap_long && (double)est[(size_t)b.perm[(size_t)n_long]] > long_tiles) n_long++;

@@ -97,6 +97,13 @@ int main(int argc, char **argv)
 
     // the device query initialises the CUDA driver (hundreds of ms): run it beside the FASTA loading
     const auto t_prog = Clock::now();
+    // checkpoints of the whole run in ms since program start (printed as one DARWIN_B200_TIMELINE line)
+    std::vector<std::pair<const char *, double>> timeline;
+    std::mutex timeline_m;
+    auto mark = [&](const char *what) {
+        std::lock_guard<std::mutex> lk(timeline_m);
+        timeline.emplace_back(what, us_since(t_prog) / 1e3);
+    };
     int ndev = 0;
     long devq_ms = 0;
     std::thread devq([&] { ndev = gact_device_count(); devq_ms = ms_since(t_prog); });
@@ -150,8 +157,10 @@ int main(int argc, char **argv)
     }
     std::cout << "Number of reads: " << num_reads << std::endl;
     std::cout << "Time elapsed (loading reads): " << ms_since(t0) << " msec" << std::endl;
+    mark("fasta_loaded");
 
     devq.join();
+    mark("cuda_driver_up");
     if (ndev <= 0) {
         fprintf(stderr, "darwin: no CUDA device available (the GACT path has no CPU fallback)\n");
         return 2;
@@ -197,7 +206,8 @@ int main(int argc, char **argv)
             upload(GACT_SET_REF, ref.seqs, 0, ref.seqs.size());
             upload(GACT_SET_READS, reads.seqs, S.first_read, S.last_read);
             upload(GACT_SET_READS_RC, rev_reads, S.first_read, S.last_read);
-            if (gact_engine_extend_supported(S.eng)) gact_engine_extend_reserve(S.eng, (int)(8 * (S.last_read - S.first_read) + 1024));
+            if (use_chains && gact_engine_extend_supported(S.eng)) gact_engine_extend_reserve(S.eng, (int)(8 * (S.last_read - S.first_read) + 1024));
+            else gact_engine_reserve_tiles(S.eng);        // tile-by-tile host scheduler: its batch slots belong to initialisation
             S.init_ms = ms_since(t_init);
         });
     }
@@ -218,6 +228,7 @@ int main(int argc, char **argv)
     }
 
     for (auto &th : init_threads) th.join();
+    mark("engines_created_sequences_uploaded");
     std::cout << "Time elapsed (GPU init" << (table_on_gpu ? "" : ", overlapped with the seed table") << "): " << ms_since(t_gpu)
               << " msec" << std::endl;
     for (auto &sh : shards) std::cout << "GPU " << sh.device << " init alone (context, engine, sequence upload): " << sh.init_ms << " msec" << std::endl;
@@ -271,6 +282,7 @@ int main(int argc, char **argv)
             });
         }
         for (auto &th : up) th.join();
+        mark("seed_tables_and_filters_ready");
         if (table_on_gpu) {
             std::cout << "Time elapsed (seed position table construction): " << ms_since(t0) << " msec" << std::endl;
             for (auto &sh : shards)
@@ -565,6 +577,7 @@ int main(int argc, char **argv)
                 });
                 for (auto &t : fmt) t.join();
                 for (auto &t : text) fout.write(t.data(), (std::streamsize)t.size());
+                sh.text.swap(text);
             }
             fout.close();
             sh.gact_ms = ms_since(tg);
@@ -617,6 +630,7 @@ int main(int argc, char **argv)
     {
         std::unique_lock<std::mutex> lk(gate_m);
         gate_cv.wait(lk, [&] { return parked == shards.size(); });
+        mark("workers_parked_bracket_opens");
         t0 = Clock::now();
         go = true;
         gate_cv.notify_all();
@@ -633,11 +647,19 @@ int main(int argc, char **argv)
         align_us = us_since(t0);
         align_ms = (long)(align_us / 1e3 + 0.5);
     }
+    mark("bracket_closes");
     const auto t_join = Clock::now();
     for (auto &w : workers) w.join();
     const long join_ms = ms_since(t_join);
+    mark("workers_joined");
     std::cout << "Time elapsed (seed table querying + aligning): " << align_ms << " msec" << std::endl;
     std::cout << "Time elapsed (worker thread exit): " << join_ms << " msec" << std::endl;
+    // The reference starts its worker threads and opens the per-thread output files inside its bracket
+    // (darwin.cpp:174-175, 615-639); here both happen before the bracket opens.  Their cost is reported so that the
+    // like-for-like figure can be formed: bracket + slowest worker set-up.
+    double setup_us = 0;
+    for (auto &sh : shards) setup_us = std::max(setup_us, sh.setup_us);
+    printf("Time elapsed (worker set-up before the bracket: thread start, device binding, output file creation): %.3f msec\n", setup_us / 1e3);
     // GPU_close comes after the timed phase in the reference as well (darwin.cpp:634-642)
     const auto t_down = Clock::now();
     for (auto &sh : shards) {
@@ -645,23 +667,78 @@ int main(int argc, char **argv)
         if (sh.seed_table) { gact_seed_table_destroy(sh.seed_table); sh.seed_table = nullptr; }
         if (sh.eng) { gact_engine_destroy(sh.eng); sh.eng = nullptr; }
     }
+    const long down_ms = ms_since(t_down);
+    mark("gpu_teardown_done");
+    std::cout << "Time elapsed (GPU teardown): " << down_ms << " msec" << std::endl;
 
-    std::cout << "Time elapsed (GPU teardown): " << ms_since(t_down) << " msec" << std::endl;
-    std::cout << "Time elapsed (program start to here): " << ms_since(t_prog) << " msec" << std::endl;
+    // f4: the sorted, duplicate-free overlap list in one file (README:32 builds it with `cat darwin.*.out | sort | uniq`;
+    // byte order = `LC_ALL=C sort`)
+    long sorted_ms = -1;
+    size_t sorted_lines = 0;
+    if (const char *sp = getenv("DARWIN_SORTED_OUT")) {
+        const auto ts = Clock::now();
+        std::vector<std::pair<const char *, size_t>> lines;
+        for (auto &sh : shards)
+            for (auto &t : sh.text) {
+                size_t a = 0;
+                while (a < t.size()) {
+                    size_t b = t.find('\n', a);
+                    if (b == std::string::npos) b = t.size();
+                    lines.emplace_back(t.data() + a, b - a);
+                    a = b + 1;
+                }
+            }
+        auto less = [](const std::pair<const char *, size_t> &x, const std::pair<const char *, size_t> &y) {
+            const int c = memcmp(x.first, y.first, std::min(x.second, y.second));
+            return c != 0 ? c < 0 : x.second < y.second;
+        };
+        std::sort(lines.begin(), lines.end(), less);
+        std::string out;
+        for (size_t i = 0; i < lines.size(); i++) {
+            if (i && lines[i].second == lines[i - 1].second && memcmp(lines[i].first, lines[i - 1].first, lines[i].second) == 0) continue;
+            out.append(lines[i].first, lines[i].second);
+            out.push_back('\n');
+            sorted_lines++;
+        }
+        std::ofstream so(sp);
+        so.write(out.data(), (std::streamsize)out.size());
+        so.close();
+        sorted_ms = ms_since(ts);
+        std::cout << "Time elapsed (sorted unique overlap file, " << sorted_lines << " lines): " << sorted_ms << " msec" << std::endl;
+    }
+    const double wall_s = std::chrono::duration<double>(Clock::now() - t_prog).count();
+    std::cout << "Time elapsed (program start to here): " << (long)(wall_s * 1e3 + 0.5) << " msec" << std::endl;
 
     int rcode = 0;
-    uint64_t tiles = 0, cells = 0;
-    double dev_ms = 0, sched_ms = 0;
+    uint64_t tiles = 0, cells = 0, cand = 0;
+    double dev_ms = 0, sched_ms = 0, init_ms = 0, table_ms = 0;
+    int batches = 0;
     for (auto &sh : shards) {
         if (!sh.error.empty()) { fprintf(stderr, "shard %d: %s\n", sh.tid, sh.error.c_str()); rcode = 3; }
-        tiles += sh.stats.tiles; cells += sh.stats.cells;
+        tiles += sh.stats.tiles; cells += sh.stats.cells; cand += sh.cand_fwd + sh.cand_rev;
         dev_ms = std::max(dev_ms, sh.stats.device_ms);
         sched_ms = std::max(sched_ms, sh.stats.wall_ms);
+        init_ms = std::max(init_ms, (double)sh.init_ms);
+        table_ms = std::max(table_ms, sh.table_kernel_ms);
+        batches = std::max(batches, sh.batches);
+    }
+    {
+        std::string tl = "DARWIN_B200_TIMELINE {";
+        for (size_t i = 0; i < timeline.size(); i++) {
+            char buf[160];
+            snprintf(buf, sizeof(buf), "%s\"%s\": %.1f", i ? ", " : "", timeline[i].first, timeline[i].second);
+            tl += buf;
+        }
+        tl += "}";
+        puts(tl.c_str());
     }
     // machine-readable summary (one line; everything above mirrors the reference's prints)
-    printf("DARWIN_B200_SUMMARY {\"reads\": %zu, \"gpus\": %zu, \"tiles\": %llu, \"cells\": %llu, \"align_phase_ms\": %ld, "
-           "\"gact_sched_ms\": %.1f, \"gact_kernel_ms\": %.1f}\n",
-           num_reads, shards.size(), (unsigned long long)tiles, (unsigned long long)cells, align_ms, sched_ms, dev_ms);
+    printf("DARWIN_B200_SUMMARY {\"reads\": %zu, \"gpus\": %zu, \"candidates\": %llu, \"tiles\": %llu, \"cells\": %llu, "
+           "\"align_phase_ms\": %.3f, \"worker_setup_ms\": %.3f, \"gact_sched_ms\": %.1f, \"gact_kernel_ms\": %.1f, "
+           "\"gpu_init_ms\": %.0f, \"seed_table_ms\": %.1f, \"teardown_ms\": %ld, \"chain_batches\": %d, \"wall_s\": %.3f, "
+           "\"sorted_unique_lines\": %zu}\n",
+           num_reads, shards.size(), (unsigned long long)cand, (unsigned long long)tiles, (unsigned long long)cells, align_us / 1e3,
+           setup_us / 1e3, sched_ms, dev_ms, init_ms, table_ms, down_ms, batches, wall_s, sorted_lines);
     delete table;
     return rcode;
 }

@@ -199,6 +199,8 @@ int gact_engine_sync(gact_engine *e);
  * (CUDA events on the engine stream); <0 if none. */
 double gact_engine_last_kernel_ms(gact_engine *e);
 
+/* Optional: allocate the batch slots of the tile path now (they are otherwise allocated by the first tile batch). */
+int gact_engine_reserve_tiles(gact_engine *e);
 int gact_engine_stats(const gact_engine *e, gact_stats *out);
 int gact_engine_reset_stats(gact_engine *e);
 

@@ -126,3 +126,44 @@ def test_acgt_reads_device_chains_match_cpu_build(tmp_path, tag, mode):
     import re
     summ = json.loads(re.search(r"DARWIN_B200_SUMMARY (\{.*\})", out).group(1))
     assert summ["tiles"] > 0 and summ["cells"] > 0
+
+
+def _gpu_count():
+    import pygact
+    return pygact.device_count()
+
+
+@pytest.mark.parametrize("gpus", [2, 4, 8])
+def test_multi_gpu_sharded_output_matches_cpu_build(tmp_path, gpus):
+    """Reads sharded over several GPUs (DARWIN_GPUS, one engine + host thread + darwin.<tid>.out per GPU): the concatenated,
+    sorted|uniq output is the reference CPU build's, whatever the shard count (config 4)."""
+    if _gpu_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    for gold, cfgs, tag in ((ACGT, ACGT_CFGS, "t320"), (GOLD, CFGS, "t320")):
+        got, out = run_darwin(str(tmp_path / f"{os.path.basename(gold)}_{gpus}"), os.path.join(gold, "ref.fasta"),
+                              os.path.join(gold, "reads.fasta"), 4, cfgs[tag], env={"DARWIN_GPUS": str(gpus)})
+        assert got == open(os.path.join(gold, f"expected_{tag}.txt")).read().splitlines()
+        assert f"Using GPU: {gpus} device(s)" in out
+        files = [fn for fn in os.listdir(str(tmp_path / f"{os.path.basename(gold)}_{gpus}")) if fn.startswith("darwin.") and fn.endswith(".out")]
+        assert len(files) == gpus
+
+
+@pytest.mark.parametrize("batch_reads", ["0", "7", "64"])
+def test_pipelined_batches_and_sorted_unique_writer(tmp_path, batch_reads):
+    """The shard's chains in batches of consecutive reads (DARWIN_BATCH_READS) give the same lines in the same order as one
+    batch, and DARWIN_SORTED_OUT writes the README:32 `sort | uniq` file directly."""
+    wd = str(tmp_path)
+    got, out = run_darwin(wd, os.path.join(ACGT, "ref.fasta"), os.path.join(ACGT, "reads.fasta"), 4, ACGT_CFGS["t320"],
+                          env={"DARWIN_BATCH_READS": batch_reads, "DARWIN_SORTED_OUT": "out.darwin"})
+    exp = open(os.path.join(ACGT, "expected_t320.txt")).read().splitlines()
+    assert got == exp
+    assert open(os.path.join(wd, "out.darwin")).read().splitlines() == exp
+    raw = open(os.path.join(wd, "darwin.0.out")).read().splitlines()
+    one, _ = run_darwin(str(tmp_path / "one"), os.path.join(ACGT, "ref.fasta"), os.path.join(ACGT, "reads.fasta"), 4,
+                        ACGT_CFGS["t320"], env={"DARWIN_BATCH_READS": "0"})
+    assert raw == open(os.path.join(str(tmp_path / "one"), "darwin.0.out")).read().splitlines()
+    import json
+    import re
+    summ = json.loads(re.search(r"DARWIN_B200_SUMMARY (\{.*\})", out).group(1))
+    assert summ["align_phase_ms"] > 0 and summ["wall_s"] > 0 and summ["sorted_unique_lines"] == len(exp)
+    assert "DARWIN_B200_TIMELINE" in out

@@ -1,6 +1,8 @@
 """Summarise an .ncu-rep (one kernel launch, --set full) into a small text file for profiles/.
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/name.txt"""
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/name.txt [profiles/name.json tiles_in_launch "capture note"]
+The optional JSON carries the raw counters bench.py turns into pipe-utilisation figures (roofline.executed)."""
 import csv
+import json
 import subprocess
 import sys
 
@@ -40,3 +42,21 @@ for name, c in sorted(ops.items(), key=lambda kv: -kv[1])[:24]:
     lines.append(f"  {name:28s} {c:14d}  {100.0 * c / tot:6.2f} %")
 open(out, "w").write("\n".join(lines) + "\n")
 print(open(out).read())
+if len(sys.argv) > 4:
+    JW = WANT + ["sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_lsu.sum",
+                 "sm__inst_executed.sum", "smsp__cycles_active.avg", "sm__cycles_active.avg", "gpc__cycles_elapsed.max"]
+    rec = {"tiles": int(sys.argv[4]), "capture": sys.argv[5] if len(sys.argv) > 5 else rep, "unit_of": {}}
+    for h, u, v in zip(hdr, units, val):
+        if h in JW:
+            try:
+                rec[h] = float(v.replace(",", ""))
+                # ncu prints byte counters in scaled units
+                scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(u)
+                if scale:
+                    rec[h] *= scale
+                rec["unit_of"][h] = u
+            except ValueError:
+                rec[h] = v
+    rec["sass_instructions_executed"] = tot
+    rec["instruction_mix"] = {k: c for k, c in sorted(ops.items(), key=lambda kv: -kv[1])[:24]}
+    json.dump(rec, open(sys.argv[3], "w"), indent=1)
