@@ -178,6 +178,52 @@ __device__ __forceinline__ void seg_stage(const SegCtx<CS, LANES> &cx, const Seq
     __syncwarp();
 }
 
+// Staging for 2-bit packed sets only (the chain kernels): both word loads are in flight together, reference and query
+// are expanded in one loop without the byte-set branches, and rb[] / qs[] hold what seg_load_q and the traceback's
+// match test expect (the ASCII encoding of seg_stage), computed from the 2-bit code by one shift.
+template <int CS, int LANES>
+__device__ __forceinline__ void seg_stage_packed(const SegCtx<CS, LANES> &cx, const SeqSetDev &rset, const SeqSetDev &qset,
+                                                 long long ref_off, int ref_len, long long query_off, int query_len,
+                                                 int reverse, int n, int m)
+{
+    __syncwarp();
+    const bool work = (n > 0 && m > 0);
+    if (work) {
+        const long long rw0 = ref_off >> 4, qw0 = query_off >> 4;
+        const int rnw = (int)(((ref_off + ref_len - 1) >> 4) - rw0) + 1;
+        const int qnw = (int)(((query_off + query_len - 1) >> 4) - qw0) + 1;
+        for (int x = cx.sl; x < max(rnw, qnw); x += LANES) {
+            uint32_t a = 0, b = 0;
+            if (x < rnw) a = __ldg(rset.packed + rw0 + x);
+            if (x < qnw) b = __ldg(qset.packed + qw0 + x);
+            if (x < rnw) cx.wr[x] = a;
+            if (x < qnw) cx.wq[x] = b;
+        }
+    }
+    __syncwarp();
+    if (work) {
+        const int ro = (int)(ref_off & 15), qo = (int)(query_off & 15);
+        // DP index x (1-based) -> position in the staged words: natural order, or back to front for reverse tiles
+        const int rbase = reverse ? ro + ref_len : ro - 1, qbase = reverse ? qo + query_len : qo - 1, step = reverse ? -1 : 1;
+        const int top = max(n + 1, m);
+        for (int x = cx.sl; x <= top; x += LANES) {
+            if (x >= 1 && x <= n + 1) {
+                const bool in = (x <= n);
+                const int pos = rbase + step * x;
+                const uint32_t code = in ? (cx.wr[pos >> 4] >> (2 * (pos & 15))) & 3u : 0u;
+                cx.rb[x] = (uint16_t)(in ? enc_base((0x54474341u >> (8 * code)) & 0xffu) : SENT_R);
+                cx.rr[x] = in ? (cx.lut_mis ^ (cx.lut_delta << (8 * code))) : cx.lut_mis;
+            }
+            if (x <= m) {
+                const int pos = qbase + step * x;
+                const uint32_t code = (x >= 1) ? (cx.wq[pos >> 4] >> (2 * (pos & 15))) & 3u : 0u;
+                cx.qs[x] = (uint16_t)((x >= 1) ? enc_base((0x54474341u >> (8 * code)) & 0xffu) : SENT_Q);
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // per-lane query registers: enc pairs (general) or PRMT selectors (LUT)
 template <int CS, int LANES, bool LUT>
 __device__ __forceinline__ void seg_load_q(const SegCtx<CS, LANES> &cx, int m, uint32_t (&q)[CS])
@@ -359,12 +405,14 @@ __device__ __forceinline__ SegTrace seg_traceback(const SegCtx<CS, LANES> &cx, c
     const int i0 = dw.i0, j0 = max(m - et, 1);
     int i = n, j = m, cnt = 0, v = corner, ri = et, rj = et;
     int col = 0, first_gap = 0, pg = prev_gap;
-    int state = (work && v > 0) ? (dw.load(i, j) >> 2) : 0;
+    // `code` is the direction code of the cell the cursor stands on whenever the cursor is in a gap state: an M run
+    // ends on a cell whose code one of the lanes has just loaded, so only a gap that goes on needs another load
+    int code = (work && v > 0) ? dw.load(i, j) : 0;
+    int state = code >> 2;
     bool act = (state != 0);
-    while (__any_sync(FULL, act)) {
+    while (LANES == 32 ? act : __any_sync(FULL, act)) {
         // one gap column (if the segment is in I or D), then the M run that follows it
         if (act && state != 3) {
-            const int code = dw.load(i, j);
             const bool open = (state == 2) ? (code & 2) : (code & 1);
             if (EMIT && sl == 0) stbuf[cnt] = (uint8_t)state;
             if (cnt == 0) first_gap = 1;
@@ -376,6 +424,7 @@ __device__ __forceinline__ SegTrace seg_traceback(const SegCtx<CS, LANES> &cx, c
             state = open ? 3 : state;
             if (i <= 0 || j <= 0) state = 0;
             act = (state != 0 && ri > 0 && rj > 0);          // the early-terminate test precedes every push (align.cpp:205-207)
+            if (act && state != 3) code = dw.load(i, j);     // the gap goes on
         }
         const bool inM = act && state == 3;
         const int it = i - sl, jt = j - sl;
@@ -383,10 +432,20 @@ __device__ __forceinline__ SegTrace seg_traceback(const SegCtx<CS, LANES> &cx, c
         const int code_t = inb ? dw.load(it, jt) : 0;
         const bool match_t = inb && (cx.rb[it] == cx.qs[jt]);
         const unsigned mm = (__ballot_sync(FULL, match_t) >> cx.segbase) & SEGMASK;
-        const int below = __popc(mm & ((1u << sl) - 1u));
-        const int v_t = v - (below * ma + (sl - below) * mi);
-        const bool isM_t = (sl == 0) || (inb && v_t > 0 && (code_t >> 2) == 3);
-        const unsigned run = (__ballot_sync(FULL, isM_t) >> cx.segbase) & SEGMASK;
+        unsigned run;
+        // Walking back over t cells lowers the score by at most t * match (mismatch <= 0 only raises it), so while
+        // v > LANES * match no cell of this step can be a zero crossing: the run length then does not depend on the scores
+        // along the diagonal and the two ballots are independent.  Only a warp-wide segment may branch on it (ballots
+        // need the whole warp).
+        if (LANES == 32 && v > LANES * ma) {
+            const bool isM_t = (sl == 0) || (inb && (code_t >> 2) == 3);
+            run = __ballot_sync(FULL, isM_t);
+        } else {
+            const int below = __popc(mm & ((1u << sl) - 1u));
+            const int v_t = v - (below * ma + (sl - below) * mi);
+            const bool isM_t = (sl == 0) || (inb && v_t > 0 && (code_t >> 2) == 3);
+            run = (__ballot_sync(FULL, isM_t) >> cx.segbase) & SEGMASK;
+        }
         int L = __ffs(~run) - 1;
         if (L < 0 || L > LANES - 1) L = LANES - 1;
         L = min(L, min(ri, rj));
@@ -399,6 +458,7 @@ __device__ __forceinline__ SegTrace seg_traceback(const SegCtx<CS, LANES> &cx, c
             v -= d; col += d;
             if (L > 0) pg = 0;
             i -= L; j -= L;
+            code = codeL;
             state = (i >= i0 && j >= j0 && v > 0) ? (codeL >> 2) : 0;
         }
         act = (state != 0 && ri > 0 && rj > 0);
@@ -766,7 +826,7 @@ gact_chain_s16h_kernel(const __grid_constant__ KParams P, const ChainCall *__res
         // ---- the tile: stage, (first pass), DP, traceback ----
         int n = have ? t_rl : 0, m = have ? t_ql : 0;
         const SeqSetDev &qset = P.sets[c.query_set];
-        seg_stage<CS, LANES, true>(cx, rset, qset, roff, t_rl, qoff, t_ql, reverse, n, m);
+        seg_stage_packed<CS, LANES>(cx, rset, qset, roff, t_rl, qoff, t_ql, reverse, n, m);
         uint32_t q[CS];
         seg_load_q<CS, LANES, true>(cx, m, q);
         PROF_MARK(1);
