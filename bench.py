@@ -184,8 +184,8 @@ def cpu_arm(args, mb, seconds, gpu_scores=None, force_port=False):
             cells = int((od["ref_len"][:k].astype(np.int64) * od["query_len"][:k]).sum())
         return cells, time.perf_counter() - t0
 
-    k0 = min(n, max(cores * 4, 64))
-    c0, t0 = run(k0)                                   # calibration (also warms the allocator)
+    k0 = min(n, max(cores * 32, 512))
+    c0, t0 = run(k0)                                   # calibration (also warms the allocator and the thread pool)
     k = int(min(n, max(k0, k0 * seconds / max(t0, 1e-3))))
     cells, t = run(k)
     if gpu_scores is not None and not (scores[:k] == gpu_scores[:k]).all():

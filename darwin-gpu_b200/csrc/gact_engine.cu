@@ -1468,3 +1468,15 @@ extern "C" int gact_prof_read(unsigned long long *out8)
     return GACT_OK;
 }
 #endif
+
+#ifdef GACT_CHECK
+// bounds-checked build only (libgact_b200_check.so): read and clear the violation counters
+extern "C" int gact_check_read(unsigned long long *out8)
+{
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaDeviceSynchronize() != cudaSuccess) return GACT_ERR_CUDA;
+    if (cudaMemcpyFromSymbol(out8, gact::g_check_fail, sizeof(z)) != cudaSuccess) return GACT_ERR_CUDA;
+    if (cudaMemcpyToSymbol(gact::g_check_fail, z, sizeof(z)) != cudaSuccess) return GACT_ERR_CUDA;
+    return GACT_OK;
+}
+#endif

@@ -10,7 +10,27 @@
 #include <type_traits>
 #include "gact_kernels_s16.cuh"
 
+// build-time tuning knobs of the wavefront loops (defaults = what measured best on B200, profiles/r2_latency_tuning.txt)
+#ifndef GACT_TAG_UNROLL
+#define GACT_TAG_UNROLL 1            // unroll factor of the tagged (window-row) loop
+#endif
+#ifndef GACT_RR_PREFETCH
+#define GACT_RR_PREFETCH 1           // fetch the next step's reference word one step ahead
+#endif
+
 namespace gact {
+
+constexpr int kTagUnroll = GACT_TAG_UNROLL;
+
+#ifdef GACT_CHECK
+// Bounds-checked build (libgact_b200_check.so, tools/sanitize_run.py): every access to the direction window and to the
+// per-segment shared-memory arrays is range-checked; violations are counted per site.  Stands in for compute-sanitizer,
+// which is closed on the GPU pool.
+__device__ unsigned long long g_check_fail[8];
+#define GACT_CHK(site, cond) do { if (!(cond)) atomicAdd(&g_check_fail[site], 1ull); } while (0)
+#else
+#define GACT_CHK(site, cond)
+#endif
 
 template <int CS>
 struct DirWinH {
@@ -24,8 +44,14 @@ struct DirWinH {
     int i0, lane0, nl;
     uint32_t *w;
     HT *h;
+#ifdef GACT_CHECK
+    int rows;                  // rows allocated (win_rows + 1)
+#endif
     __device__ __forceinline__ void init(void *base, int n, int m, const KParams &P)
     {
+#ifdef GACT_CHECK
+        rows = P.win_rows + 1;
+#endif
         i0 = max(n - P.et, 1);
         const int j0 = max(m - P.et, 1);
         lane0 = ((j0 - 1) / CS) >> 1;
@@ -45,6 +71,7 @@ struct DirWinH {
         const int s = (j - 1) / CS, c = (j - 1) - s * CS;
         const int lane = s >> 1, half = s & 1;
         const int e = (i + half - i0) * nl + (lane - lane0);
+        GACT_CHK(0, i + half - i0 >= 0 && i + half - i0 < rows && lane - lane0 >= 0 && lane - lane0 < nl);
         if (c < NW * 4) return (w[e * NW + (c >> 2)] >> (16 * half + 4 * (3 - (c & 3)))) & 15;
         if (R == 1) return (h[e] >> (4 * half)) & 15;
         return (h[e] >> (8 * half + 4 * (R - 1 - (c - NW * 4)))) & 15;
@@ -290,6 +317,7 @@ __device__ __forceinline__ int seg_dp(const SegCtx<CS, LANES> &cx, const uint32_
     }
     uint32_t eG = Bp, eD = pk16(S16_NEG), diag = Bp;
     uint32_t rprev = LUT ? rrp[0] : 0u;                 // reference word of the previous step = this step's high half
+    uint32_t rnext = rrp[1];                            // this step's word, fetched one step ahead (GACT_RR_PREFETCH)
     int k = 1;
     for (; k <= k1; k++) {
         const uint32_t pack = __byte_perm(eG, eD, 0x7632);
@@ -297,7 +325,9 @@ __device__ __forceinline__ int seg_dp(const SegCtx<CS, LANES> &cx, const uint32_
         if (sl == 0) recv = cx.borderD_raw;
         const uint32_t inG = __byte_perm(recv, eG, 0x5410);
         const uint32_t inD = __byte_perm(recv, eD, 0x5432);
-        const uint32_t rlo = rrp[k], rhi = rprev;
+        GACT_CHK(2, k - 2 * sl >= -cx.PAD && k + 1 - 2 * sl < cx.TS + 2 + cx.PAD);
+        const uint32_t rlo = GACT_RR_PREFETCH ? rnext : rrp[k], rhi = rprev;
+        if (GACT_RR_PREFETCH) rnext = rrp[k + 1];
         uint32_t hd = diag, dv = inD;
 #pragma unroll
         for (int c = 0; c < CS; c++) {
@@ -331,13 +361,16 @@ __device__ __forceinline__ int seg_dp(const SegCtx<CS, LANES> &cx, const uint32_
     // the loop stops at the corner step of each segment (at most two different ones per warp) so that the corner
     // value is picked out of the registers outside the loop
     for (int stop = kc_min;; stop = steps) {
+#pragma unroll (kTagUnroll)
     for (; k <= stop; k++) {
         const uint32_t pack = __byte_perm(eG, eD, 0x7632);
         uint32_t recv = __shfl_up_sync(FULL, pack, 1, LANES);
         if (sl == 0) recv = cx.borderD_tag;
         const uint32_t inG = __byte_perm(recv, eG, 0x5410);
         const uint32_t inD = __byte_perm(recv, eD, 0x5432);
-        const uint32_t rlo = rrp[k], rhi = rprev;
+        GACT_CHK(2, k - 2 * sl >= -cx.PAD && k + 1 - 2 * sl < cx.TS + 2 + cx.PAD);
+        const uint32_t rlo = GACT_RR_PREFETCH ? rnext : rrp[k], rhi = rprev;
+        if (GACT_RR_PREFETCH) rnext = rrp[k + 1];
         uint32_t hd = diag, dv = inD;
         uint32_t acc[NW + 1];
 #pragma unroll
@@ -359,6 +392,8 @@ __device__ __forceinline__ int seg_dp(const SegCtx<CS, LANES> &cx, const uint32_
         diag = inG;
         if (LUT) rprev = rlo;
         if (k >= kstore && k <= kend) {
+            GACT_CHK(1, k - 2 * sl - dw.i0 >= 0 && k - 2 * sl - dw.i0 < dw.rows && sl - dw.lane0 >= 0 && sl - dw.lane0 < dw.nl &&
+                            wptr == dw.w + ((k - 2 * sl - dw.i0) * dw.nl + (sl - dw.lane0)) * NW);
 #pragma unroll
             for (int x = 0; x < NW; x++) wptr[x] = acc[x];
             if (R) *hptr = DirWinH<CS>::pack_rest(acc[NW]);
@@ -430,6 +465,7 @@ __device__ __forceinline__ SegTrace seg_traceback(const SegCtx<CS, LANES> &cx, c
         const int it = i - sl, jt = j - sl;
         const bool inb = inM && it >= i0 && jt >= j0;
         const int code_t = inb ? dw.load(it, jt) : 0;
+        GACT_CHK(3, !inb || (it >= 1 && it <= cx.TS + 1 && jt >= 1 && jt <= cx.TS + 1));
         const bool match_t = inb && (cx.rb[it] == cx.qs[jt]);
         const unsigned mm = (__ballot_sync(FULL, match_t) >> cx.segbase) & SEGMASK;
         unsigned run;
@@ -451,6 +487,7 @@ __device__ __forceinline__ SegTrace seg_traceback(const SegCtx<CS, LANES> &cx, c
         L = min(L, min(ri, rj));
         const int codeL = __shfl_sync(FULL, code_t, cx.segbase + L);
         if (inM) {
+            GACT_CHK(4, !EMIT || cnt + L <= 2 * et);
             if (EMIT && sl < L) stbuf[cnt + sl] = 3;
             const int bl = __popc(mm & ((1u << L) - 1u));
             const int d = bl * ma + (L - bl) * mi;
