@@ -1,10 +1,15 @@
 // gact_common.cuh -- device-side types shared by the GACT tile kernels.
 //
 // Data layout in HBM
-//   * sequence sets: one concatenated buffer per set, either 2-bit packed
-//     (16 bases per 32-bit word, base b at bits [2b, 2b+1], A=0 C=1 G=2 T=3) or
-//     one byte per base when the set holds anything but ACGT (the reference
-//     compares raw bytes, align.cpp:134);
+//   * sequence sets: one concatenated buffer per set, 2-bit packed (16 bases per
+//     32-bit word, base b at bits [2b, 2b+1], A/a=0 C/c=1 G/g=2 T/t=3, anything
+//     else 0: the coding of ntcoding.cpp:60-72, which is what D-SOFT hashes).  A set
+//     that holds any byte other than upper-case ACGT also keeps an EXCEPTION bitmap
+//     (1 bit per base) and its raw bytes: the reference compares raw bytes
+//     (align.cpp:134: 'N'=='N' matches, 'a'!='A'), so the one-PRMT score table is
+//     exact only where the query window has no exception (an exception in the
+//     reference window then mismatches every query base); tiles whose query window
+//     holds one run on the raw-byte kernels;
 //   * tile descriptors: gact_tile_desc (32 B, include/gact_b200.h);
 //   * results: gact_tile_result (24 B) + 2-bit packed traceback states.
 #pragma once
@@ -15,8 +20,9 @@
 namespace gact {
 
 struct SeqSetDev {
-    const uint32_t *packed;   // 2-bit words, or nullptr
-    const uint8_t *bytes;     // raw bytes, or nullptr
+    const uint32_t *packed;   // 2-bit words (nullptr for an empty set)
+    const uint8_t *bytes;     // raw bytes, only for sets with exceptions (else nullptr)
+    const uint32_t *exc;      // exception bitmap, bit b of word w = base 32 w + b is not one of "ACGT" (else nullptr)
     long long len;
 };
 
@@ -39,6 +45,7 @@ static constexpr int NEG_BORDER = -(1 << 30);     // align.h:18
 
 __device__ __forceinline__ int fetch_base(const SeqSetDev &s, long long idx)
 {
+    if (s.bytes) return __ldg(s.bytes + idx);       // raw bytes where the set has exceptions
     if (s.packed) {
         const uint32_t w = __ldg(s.packed + (idx >> 4));
         const int code = (w >> (2 * (int)(idx & 15))) & 3;

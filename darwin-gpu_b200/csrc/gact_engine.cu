@@ -27,11 +27,27 @@ namespace {
 thread_local std::string g_create_error;
 
 struct SeqSetHost {
-    uint32_t *d_packed = nullptr;
-    uint8_t *d_bytes = nullptr;
+    uint32_t *d_packed = nullptr;             // always (non-empty sets)
+    uint8_t *d_bytes = nullptr;               // raw bytes, only when the set holds a byte other than ACGT
+    uint32_t *d_exc = nullptr;                // exception bitmap, ditto
     long long len = 0;
-    int bits = 0;
+    int bits = 0;                             // 2: ACGT only; 8: raw bytes kept beside the packed words
     std::vector<long long> starts;
+    std::vector<uint32_t> h_exc;              // host copy of the bitmap (empty: no exception)
+    std::vector<uint8_t> seq_exc;             // per sequence: holds an exception
+    // any exception among bases [off, off + n)?
+    bool range_has_exc(long long off, long long n) const
+    {
+        if (h_exc.empty() || n <= 0) return false;
+        const long long w0 = off >> 5, w1 = (off + n - 1) >> 5;
+        for (long long w = w0; w <= w1; w++) {
+            uint32_t v = h_exc[(size_t)w];
+            if (w == w0) v &= 0xffffffffu << (off & 31);
+            if (w == w1 && ((off + n) & 31)) v &= 0xffffffffu >> (32 - ((off + n) & 31));
+            if (v) return true;
+        }
+        return false;
+    }
 };
 
 struct Slot {
@@ -41,7 +57,9 @@ struct Slot {
     EffLen *d_eff = nullptr;
     int *d_first = nullptr, *h_first = nullptr;
     int *d_order = nullptr, *h_order = nullptr;      // tiles by descending reference length (pairs similar tiles)
-    int *d_counters = nullptr;            // [0] first pass, [1] main pass
+    int *d_counters = nullptr;            // [0] first pass, [1] main pass, [2] / [3] the same for the raw-byte group
+    int n_lut = 0, n_first_lut = 0;       // tiles / first tiles whose query window has no exception: they come first in
+                                          // h_order / h_first and run on the score-table kernels, the rest on raw bytes
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr, ev_h2d = nullptr, ev_fork = nullptr;
     int n = 0, n_first = 0;
     bool busy = false;
@@ -101,40 +119,46 @@ int fail(gact_engine *e, int code, const std::string &msg)
     } while (0)
 
 // --------------------------------------------------------------------------
-// upload: raw bytes -> 2-bit words, and "is everything ACGT?" in one pass
+// upload: raw bytes -> 2-bit words (ntcoding.cpp:60-72: case folded, anything else 0) + exception bitmap (one bit
+// per base that is not one of "ACGT") in one pass; one thread per 32 bases
 __global__ void pack2_kernel(const uint8_t *__restrict__ raw, long long len, uint32_t *__restrict__ packed,
-                             long long n_words, int *not_acgt)
+                             uint32_t *__restrict__ exc, long long n_exc_words, int *any_exc)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
     int bad = 0;
-    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
-        uint32_t v = 0;
-        const long long b0 = w * 16;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < n_exc_words; w += stride) {
+        uint32_t lo = 0, hi = 0, ex = 0;
+        const long long b0 = w * 32;
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
+        for (int k = 0; k < 32; k++) {
             const long long idx = b0 + k;
             if (idx < len) {
                 const int ch = raw[idx];
-                int code;
-                switch (ch) {
-                    case 'A': code = 0; break;
-                    case 'C': code = 1; break;
-                    case 'G': code = 2; break;
-                    case 'T': code = 3; break;
-                    default: code = 0; bad = 1; break;
+                uint32_t code = 0;
+                switch (ch | 0x20) {
+                    case 'a': code = 0; break;
+                    case 'c': code = 1; break;
+                    case 'g': code = 2; break;
+                    case 't': code = 3; break;
+                    default: code = 0; break;
                 }
-                v |= (uint32_t)code << (2 * k);
+                if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') ex |= 1u << k;
+                if (k < 16) lo |= code << (2 * k); else hi |= code << (2 * (k - 16));
             }
         }
-        packed[w] = v;
+        packed[2 * w] = lo;
+        packed[2 * w + 1] = hi;
+        exc[w] = ex;
+        bad |= (ex != 0);
     }
-    if (bad) atomicOr(not_acgt, 1);
+    if (bad) atomicOr(any_exc, 1);
 }
 
 void free_set(SeqSetHost &s)
 {
     if (s.d_packed) cudaFree(s.d_packed);
     if (s.d_bytes) cudaFree(s.d_bytes);
+    if (s.d_exc) cudaFree(s.d_exc);
     s = SeqSetHost();
 }
 
@@ -261,24 +285,40 @@ bool use_s16(const gact_engine *e)
 int launch_batch(gact_engine *e, Slot &s, cudaStream_t st, int scratch_region)
 {
     CU(e, cudaStreamWaitEvent(st, s.ev_h2d, 0));        // descriptors of this batch are on the device
-    CU(e, cudaMemsetAsync(s.d_counters, 0, 2 * sizeof(int), st));
+    CU(e, cudaMemsetAsync(s.d_counters, 0, 4 * sizeof(int), st));
     CU(e, cudaEventRecord(s.ev_k0, st));
     const int TS = e->C * 32;
-    if (s.n_first > 0 && use_s16(e)) {
-        s16h_launch_first(e->s16h, e->kp, s.d_descs, s.d_first, s.n_first, s.d_eff, s.d_counters + 0, st);
-        e->stats.kernel_launches++;
-    } else if (s.n_first > 0) {
-        first_fn ff = pick_first_i32(e->C);
-        int ctas = e->num_sms * 4;
-        int need = (s.n_first + 7) / 8;
-        if (need < ctas) ctas = need;
-        ff<<<ctas, 256, 8 * TS, st>>>(e->kp, s.d_descs, s.d_first, s.n_first, s.d_eff, s.d_counters + 0);
-        e->stats.kernel_launches++;
-    }
     if (use_s16(e)) {
-        s16h_launch(e->s16h, e->kp, s.d_descs, s.d_order, s.n, s.d_eff, s.d_results, s.d_states, e->pitch_words,
-                    s.d_counters + 1, st, scratch_region);
+        // two groups (check_descs): tiles whose query window is free of exceptions score with the one-PRMT table from the
+        // packed words; the others compare raw bytes (HSET2 path).  Same kernels otherwise, results land at the tile's index.
+        const int n_byte = s.n - s.n_lut, nf_byte = s.n_first - s.n_first_lut;
+        if (s.n_first_lut > 0) {
+            s16h_launch_first(e->s16h, e->kp, s.d_descs, s.d_first, s.n_first_lut, s.d_eff, s.d_counters + 0, st, true);
+            e->stats.kernel_launches++;
+        }
+        if (nf_byte > 0) {
+            s16h_launch_first(e->s16h, e->kp, s.d_descs, s.d_first + s.n_first_lut, nf_byte, s.d_eff, s.d_counters + 2, st, false);
+            e->stats.kernel_launches++;
+        }
+        if (s.n_lut > 0) {
+            s16h_launch(e->s16h, e->kp, s.d_descs, s.d_order, s.n_lut, s.d_eff, s.d_results, s.d_states, e->pitch_words,
+                        s.d_counters + 1, st, scratch_region, true);
+            e->stats.kernel_launches++;
+        }
+        if (n_byte > 0) {
+            s16h_launch(e->s16h, e->kp, s.d_descs, s.d_order + s.n_lut, n_byte, s.d_eff, s.d_results, s.d_states, e->pitch_words,
+                        s.d_counters + 3, st, scratch_region, false);
+            e->stats.kernel_launches++;
+        }
     } else {
+        if (s.n_first > 0) {
+            first_fn ff = pick_first_i32(e->C);
+            int ctas = e->num_sms * 4;
+            int need = (s.n_first + 7) / 8;
+            if (need < ctas) ctas = need;
+            ff<<<ctas, 256, 8 * TS, st>>>(e->kp, s.d_descs, s.d_first, s.n_first, s.d_eff, s.d_counters + 0);
+            e->stats.kernel_launches++;
+        }
         main_fn f = pick_main_i32(e->C, e->dir_global);
         int ctas = e->ctas;
         int need = (s.n + e->warps_per_cta - 1) / e->warps_per_cta;
@@ -286,8 +326,8 @@ int launch_batch(gact_engine *e, Slot &s, cudaStream_t st, int scratch_region)
         f<<<ctas, e->warps_per_cta * 32, e->smem_main, st>>>(e->kp, s.d_descs, s.n, s.d_eff, s.d_results,
                                                              s.d_states, e->pitch_words, s.d_counters + 1,
                                                              e->d_gscratch, e->per_warp_bytes);
+        e->stats.kernel_launches++;
     }
-    e->stats.kernel_launches++;
     CU(e, cudaGetLastError());
     CU(e, cudaEventRecord(s.ev_k1, st));
     return GACT_OK;
@@ -296,25 +336,36 @@ int launch_batch(gact_engine *e, Slot &s, cudaStream_t st, int scratch_region)
 int check_descs(gact_engine *e, int n, const gact_tile_desc *descs, Slot &s)
 {
     const int T = e->params.tile_size;
-    int nf = 0;
     unsigned long long cells = 0;
+    const bool table_ok = use_s16(e) && e->s16h.lut_ok;
+    // group 0: score-table kernels, group 1: raw-byte kernels
+    std::vector<uint8_t> grp((size_t)n, 0);
+    int cnt[2] = {0, 0}, nf[2] = {0, 0};
     for (int t = 0; t < n; t++) {
         const gact_tile_desc &d = descs[t];
         if (d.ref_set >= GACT_MAX_SETS || d.query_set >= GACT_MAX_SETS || d.ref_len < 0 || d.query_len < 0 ||
             d.ref_len > T || d.query_len > T || d.ref_off < 0 || d.query_off < 0 ||
             d.ref_off + d.ref_len > e->sets[d.ref_set].len || d.query_off + d.query_len > e->sets[d.query_set].len)
             return fail(e, GACT_ERR_ARG, "tile descriptor " + std::to_string(t) + " out of range");
-        if (d.first) s.h_first[nf++] = t;
+        const int g = (table_ok && !e->sets[d.query_set].range_has_exc(d.query_off, d.query_len)) ? 0 : 1;
+        grp[(size_t)t] = (uint8_t)g;
+        cnt[g]++;
+        if (d.first) nf[g]++;
         cells += (unsigned long long)d.ref_len * (unsigned long long)d.query_len;
     }
-    s.n_first = nf;
+    s.n_lut = cnt[0];
+    s.n_first_lut = nf[0];
+    s.n_first = nf[0] + nf[1];
     s.cells = cells;
-    // counting sort by reference length, longest first: the two tiles a warp aligns side by side
+    int fpos[2] = {0, nf[0]};
+    for (int t = 0; t < n; t++) if (descs[t].first) s.h_first[fpos[grp[(size_t)t]]++] = t;
+    // counting sort by reference length inside each group, longest first: the two tiles a warp aligns side by side
     // then have the same number of wavefront steps, and the long tiles start first
-    std::vector<int> start((size_t)T + 2, 0);
-    for (int t = 0; t < n; t++) start[(size_t)(T - descs[t].ref_len) + 1]++;
-    for (int k = 1; k <= T + 1; k++) start[k] += start[k - 1];
-    for (int t = 0; t < n; t++) s.h_order[start[(size_t)(T - descs[t].ref_len)]++] = t;
+    std::vector<int> start(2 * ((size_t)T + 2), 0);
+    auto bucket = [&](int t) { return (size_t)grp[(size_t)t] * ((size_t)T + 1) + (size_t)(T - descs[t].ref_len); };
+    for (int t = 0; t < n; t++) start[bucket(t) + 1]++;
+    for (size_t k = 1; k < start.size(); k++) start[k] += start[k - 1];
+    for (int t = 0; t < n; t++) s.h_order[start[bucket(t)]++] = t;
     return GACT_OK;
 }
 
@@ -385,7 +436,7 @@ int ensure_slots(gact_engine *e)
         CU(e, cudaMalloc(&s.d_first, n * sizeof(int)));
         CU(e, cudaMalloc(&s.d_order, n * sizeof(int)));
         CU(e, cudaMallocHost(&s.h_order, n * sizeof(int)));
-        CU(e, cudaMalloc(&s.d_counters, 2 * sizeof(int)));
+        CU(e, cudaMalloc(&s.d_counters, 4 * sizeof(int)));
         CU(e, cudaMallocHost(&s.h_descs, n * sizeof(gact_tile_desc)));
         CU(e, cudaMallocHost(&s.h_results, n * sizeof(gact_tile_result)));
         CU(e, cudaMallocHost(&s.h_states, n * e->pitch_words * 4));
@@ -479,7 +530,7 @@ int gact_engine_create(gact_engine **out, int device, const gact_params *p, int 
         e->kp.match = p->match; e->kp.mismatch = p->mismatch;
         e->kp.gap_open = p->gap_open; e->kp.gap_extend = p->gap_extend;
         e->kp.et = et; e->kp.tile_size = p->tile_size;
-        for (int i = 0; i < GACT_MAX_SETS; i++) e->kp.sets[i] = SeqSetDev{nullptr, nullptr, 0};
+        for (int i = 0; i < GACT_MAX_SETS; i++) e->kp.sets[i] = SeqSetDev{nullptr, nullptr, nullptr, 0};
 
         rc = plan_launch(e);
         if (rc) { g_create_error = e->err; goto bad; }
@@ -523,7 +574,7 @@ int gact_engine_upload(gact_engine *e, int set, int64_t n_seqs, const char *cons
     CU(e, cudaStreamSynchronize(e->stream));
     SeqSetHost &s = e->sets[set];
     free_set(s);
-    e->kp.sets[set] = SeqSetDev{nullptr, nullptr, 0};
+    e->kp.sets[set] = SeqSetDev{nullptr, nullptr, nullptr, 0};
     // the set becomes visible (len, starts, device pointers) only once every step below has succeeded: a failed
     // upload leaves it empty, so descriptor validation rejects tiles that would address it
     long long total = 0;
@@ -534,7 +585,7 @@ int gact_engine_upload(gact_engine *e, int set, int64_t n_seqs, const char *cons
         total += lens[i];
     }
     starts[(size_t)n_seqs] = total;
-    if (total == 0) { s.starts = starts; s.len = 0; s.bits = 0; return GACT_OK; }
+    if (total == 0) { s.starts = starts; s.len = 0; s.bits = 0; s.seq_exc.assign((size_t)n_seqs, 0); return GACT_OK; }
 
     // stage through pinned memory in chunks, concatenating on the device
     uint8_t *d_raw = nullptr;
@@ -569,27 +620,45 @@ int gact_engine_upload(gact_engine *e, int set, int64_t n_seqs, const char *cons
     if (rc != GACT_OK) { cudaFree(d_raw); return rc; }
     e->stats.h2d_bytes += (double)total;
 
-    const long long n_words = (total + 15) / 16 + 1;     // +1 pad word: tiles may peek past the end
-    uint32_t *d_packed = nullptr;
+    const long long n_exc_words = (total + 31) / 32;
+    const long long n_words = 2 * n_exc_words + 2;       // pad words: tiles may peek past the end
+    uint32_t *d_packed = nullptr, *d_exc = nullptr;
     int *d_flag = nullptr;
-    if (cudaMalloc(&d_packed, (size_t)n_words * 4) != cudaSuccess || cudaMalloc(&d_flag, sizeof(int)) != cudaSuccess) {
-        cudaGetLastError(); cudaFree(d_raw); if (d_packed) cudaFree(d_packed);
+    if (cudaMalloc(&d_packed, (size_t)n_words * 4) != cudaSuccess || cudaMalloc(&d_exc, (size_t)(n_exc_words + 2) * 4) != cudaSuccess ||
+        cudaMalloc(&d_flag, sizeof(int)) != cudaSuccess) {
+        cudaGetLastError(); cudaFree(d_raw); if (d_packed) cudaFree(d_packed); if (d_exc) cudaFree(d_exc);
         return fail(e, GACT_ERR_NOMEM, "cudaMalloc(packed bases) failed");
     }
     int h_flag = 0;
     cudaMemsetAsync(d_flag, 0, sizeof(int), e->stream);
     cudaMemsetAsync(d_packed, 0, (size_t)n_words * 4, e->stream);
-    int blocks = (int)std::min<long long>((n_words + 255) / 256, (long long)e->num_sms * 8);
-    pack2_kernel<<<blocks, 256, 0, e->stream>>>(d_raw, total, d_packed, n_words - 1, d_flag);
+    cudaMemsetAsync(d_exc, 0, (size_t)(n_exc_words + 2) * 4, e->stream);
+    int blocks = (int)std::min<long long>((n_exc_words + 255) / 256, (long long)e->num_sms * 8);
+    pack2_kernel<<<blocks, 256, 0, e->stream>>>(d_raw, total, d_packed, d_exc, n_exc_words, d_flag);
     cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
     cudaError_t r = cudaStreamSynchronize(e->stream);
     cudaFree(d_flag);
-    if (r != cudaSuccess) { cudaFree(d_raw); cudaFree(d_packed); return fail(e, GACT_ERR_CUDA, std::string("pack kernel: ") + cudaGetErrorString(r)); }
-    if (h_flag) { cudaFree(d_packed); s.d_bytes = d_raw; s.bits = 8; }
-    else        { cudaFree(d_raw); s.d_packed = d_packed; s.bits = 2; }
+    if (r != cudaSuccess) { cudaFree(d_raw); cudaFree(d_packed); cudaFree(d_exc); return fail(e, GACT_ERR_CUDA, std::string("pack kernel: ") + cudaGetErrorString(r)); }
+    std::vector<uint32_t> h_exc;
+    std::vector<uint8_t> seq_exc((size_t)n_seqs, 0);
+    if (h_flag) {
+        // sets with exceptions keep the bitmap (device + host copy) and the raw bytes for the byte-comparing kernels
+        h_exc.resize((size_t)n_exc_words + 2, 0);
+        r = cudaMemcpy(h_exc.data(), d_exc, (size_t)n_exc_words * 4, cudaMemcpyDeviceToHost);
+        if (r != cudaSuccess) { cudaFree(d_raw); cudaFree(d_packed); cudaFree(d_exc); return fail(e, GACT_ERR_CUDA, std::string("exception bitmap copy: ") + cudaGetErrorString(r)); }
+        s.d_bytes = d_raw; s.d_exc = d_exc; s.bits = 8;
+        e->stats.d2h_bytes += (double)n_exc_words * 4;
+    } else {
+        cudaFree(d_raw); cudaFree(d_exc); s.bits = 2;
+    }
+    s.d_packed = d_packed;
+    s.h_exc.swap(h_exc);
     s.starts.swap(starts);
     s.len = total;
-    e->kp.sets[set] = SeqSetDev{s.d_packed, s.d_bytes, s.len};
+    if (h_flag)
+        for (int64_t i = 0; i < n_seqs; i++) seq_exc[(size_t)i] = s.range_has_exc(s.starts[(size_t)i], lens[i]) ? 1 : 0;
+    s.seq_exc.swap(seq_exc);
+    e->kp.sets[set] = SeqSetDev{s.d_packed, s.d_bytes, s.d_exc, s.len};
     return GACT_OK;
 }
 
@@ -604,6 +673,13 @@ int64_t gact_engine_set_length(const gact_engine *e, int set)
 {
     if (!e || set < 0 || set >= GACT_MAX_SETS) return -1;
     return e->sets[set].len;
+}
+int gact_engine_seq_has_exceptions(const gact_engine *e, int set, int64_t i)
+{
+    if (!e || set < 0 || set >= GACT_MAX_SETS) return -1;
+    const SeqSetHost &s = e->sets[set];
+    if (i < 0 || (size_t)i + 1 >= s.starts.size()) return -1;
+    return (!s.seq_exc.empty() && s.seq_exc[(size_t)i]) ? 1 : 0;
 }
 int gact_engine_set_bits(const gact_engine *e, int set)
 {
@@ -1229,8 +1305,9 @@ extern "C" {
 
 int gact_engine_extend_supported(const gact_engine *e)
 {
+    // exceptions (bytes other than ACGT) in the reference are handled inside the chain kernels; a QUERY sequence that holds
+    // one must go through the tile path (gact_engine_seq_has_exceptions tells which)
     if (!e || !e->s16h.ok || !e->s16h.lut_ok || e->variant_req == 1) return 0;
-    for (int i = 0; i < GACT_MAX_SETS; i++) if (e->sets[i].bits == 8) return 0;
     return 1;
 }
 
@@ -1307,6 +1384,9 @@ int gact_engine_extend_submit(gact_engine *e, int n, const gact_call *calls)
             const long long rl = rs.starts[(size_t)c.ref_seq + 1] - rs.starts[(size_t)c.ref_seq];
             if (c.ref_pos < 0 || c.query_pos < 0 || c.ref_pos > rl || c.query_pos > ql)
                 return fail(e, GACT_ERR_ARG, "call " + std::to_string(i) + ": anchor outside its sequences");
+            if (!qs.seq_exc.empty() && qs.seq_exc[(size_t)c.query_seq])
+                return fail(e, GACT_ERR_ARG, "call " + std::to_string(i) + ": the query sequence holds bytes other than ACGT "
+                                             "(gact_engine_seq_has_exceptions); extend it through the tile path");
             est[(size_t)i] = (int)std::min<long long>(std::min(ql, rl) / et + 2, 1 << 20);
             est_max = std::max(est_max, est[(size_t)i]);
             est_sum += est[(size_t)i];

@@ -12,15 +12,16 @@
 
 // build-time tuning knobs of the wavefront loops (defaults = what measured best on B200, profiles/r2_latency_tuning.txt)
 #ifndef GACT_TAG_UNROLL
-#define GACT_TAG_UNROLL 1            // unroll factor of the tagged (window-row) loop
-#endif
+#define GACT_TAG_UNROLL 4            // unroll factor of the tagged (window-row) loop of the latency kernels (one warp alone on
+#endif                               // a sub-partition: 50.6 k -> 44.1 k cycles per tile); the throughput kernels use 2 (+1 %)
 #ifndef GACT_RR_PREFETCH
 #define GACT_RR_PREFETCH 1           // fetch the next step's reference word one step ahead
 #endif
 
 namespace gact {
 
-constexpr int kTagUnroll = GACT_TAG_UNROLL;
+template <int CS, int LANES>
+struct TagUnroll { static constexpr int value = (LANES == 32 && CS <= 5) ? GACT_TAG_UNROLL : 2; };
 
 #ifdef GACT_CHECK
 // Bounds-checked build (libgact_b200_check.so, tools/sanitize_run.py): every access to the direction window and to the
@@ -94,7 +95,7 @@ struct DirWinH {
 __host__ __device__ constexpr size_t s16h_seq_bytes(int CS, int LANES)
 {
     const int TS = CS * 2 * LANES, PAD = 2 * LANES;
-    return (size_t)((((PAD + TS + 2 + PAD) * 4 + (TS + 2) * 4) + 15) & ~15) + (size_t)((2 * (TS / 16 + 2) * 4 + 15) & ~15);
+    return (size_t)((((PAD + TS + 2 + PAD) * 4 + (TS + 2) * 4) + 15) & ~15) + (size_t)(((2 * (TS / 16 + 2) + (TS / 32 + 2)) * 4 + 15) & ~15);
 }
 
 template <int CS, int LANES>
@@ -105,6 +106,7 @@ struct SegCtx {
     uint32_t *rr;            // rr[i]: substitution table of R[i] (LUT) or enc(R[i]) | enc(R[i-1]) << 16
     uint16_t *qs, *rb;       // enc(Q[j]), enc(R[i])
     uint32_t *wr, *wq;       // the tile's 2-bit packed words as loaded from HBM (reference / query), <= TS/16 + 2 each
+    uint32_t *we;            // exception bitmap words of the reference window (<= TS/32 + 2), sets with exceptions only
     void *dirbase;
     // constants of the biased x16 domain
     int B, KO, KI, KD, ONE, et, match, mismatch, gap_open, gap_extend;
@@ -125,6 +127,7 @@ struct SegCtx {
         rb = qs + (TS + 2);
         wr = reinterpret_cast<uint32_t *>(my + ((((PAD + TS + 2 + PAD) * 4 + (TS + 2) * 4) + 15) & ~15));
         wq = wr + (TS / 16 + 2);
+        we = wq + (TS / 16 + 2);
         // direction window: per-segment global scratch, or (SMEMWIN) the shared memory behind this segment's sequence arrays
         if (SMEMWIN) dirbase = (void *)(my + s16h_seq_bytes(CS, LANES));
         else dirbase = gscratch ? (void *)(gscratch + ((size_t)global_warp * TPW + seg) * dir_bytes) : nullptr;
@@ -166,12 +169,13 @@ __device__ __forceinline__ void seg_stage(const SegCtx<CS, LANES> &cx, const Seq
 {
     __syncwarp();
     const bool work = (n > 0 && m > 0);
-    if (work && rset.packed) {
+    const bool rpk = rset.packed && !rset.bytes, qpk = qset.packed && !qset.bytes;    // raw bytes win where a set keeps them
+    if (work && rpk) {
         const long long w0 = ref_off >> 4;
         const int nw = (int)(((ref_off + ref_len - 1) >> 4) - w0) + 1;
         for (int x = cx.sl; x < nw; x += LANES) cx.wr[x] = __ldg(rset.packed + w0 + x);
     }
-    if (work && qset.packed) {
+    if (work && qpk) {
         const long long w0 = query_off >> 4;
         const int nw = (int)(((query_off + query_len - 1) >> 4) - w0) + 1;
         for (int x = cx.sl; x < nw; x += LANES) cx.wq[x] = __ldg(qset.packed + w0 + x);
@@ -181,8 +185,8 @@ __device__ __forceinline__ void seg_stage(const SegCtx<CS, LANES> &cx, const Seq
         const int ro = (int)(ref_off & 15), qo = (int)(query_off & 15);
         for (int x = 1 + cx.sl; x <= n + 1; x += LANES) {
             const bool in = (x <= n);
-            const int base = !in ? 0 : rset.packed ? smem_base(cx.wr, ro, ref_len, reverse, x)
-                                                   : tile_base(rset, ref_off, ref_len, reverse, x);
+            const int base = !in ? 0 : rpk ? smem_base(cx.wr, ro, ref_len, reverse, x)
+                                           : tile_base(rset, ref_off, ref_len, reverse, x);
             cx.rb[x] = (uint16_t)(in ? enc_base(base) : SENT_R);
             if (LUT) {
                 const int code = (base == 'A') ? 0 : (base == 'C') ? 1 : (base == 'G') ? 2 : (base == 'T') ? 3 : 4;
@@ -192,8 +196,8 @@ __device__ __forceinline__ void seg_stage(const SegCtx<CS, LANES> &cx, const Seq
             }
         }
         for (int x = cx.sl; x <= m; x += LANES) {
-            const int base = x < 1 ? 0 : qset.packed ? smem_base(cx.wq, qo, query_len, reverse, x)
-                                                     : tile_base(qset, query_off, query_len, reverse, x);
+            const int base = x < 1 ? 0 : qpk ? smem_base(cx.wq, qo, query_len, reverse, x)
+                                             : tile_base(qset, query_off, query_len, reverse, x);
             cx.qs[x] = (x >= 1) ? (uint16_t)enc_base(base) : (uint16_t)SENT_Q;
         }
     }
@@ -205,9 +209,12 @@ __device__ __forceinline__ void seg_stage(const SegCtx<CS, LANES> &cx, const Seq
     __syncwarp();
 }
 
-// Staging for 2-bit packed sets only (the chain kernels): both word loads are in flight together, reference and query
-// are expanded in one loop without the byte-set branches, and rb[] / qs[] hold what seg_load_q and the traceback's
-// match test expect (the ASCII encoding of seg_stage), computed from the 2-bit code by one shift.
+// Staging from the 2-bit packed words (every kernel that scores with the one-PRMT table): both word loads are in flight
+// together, reference and query are expanded in one loop without the byte-set branches, and rb[] / qs[] hold what
+// seg_load_q and the traceback's match test expect (the ASCII encoding of seg_stage), computed from the 2-bit code by
+// one shift.  The query window must be free of exceptions (the host routes other tiles to the raw-byte kernels); a
+// reference base that is an exception (rset.exc) becomes a sentinel row: it mismatches every query base, exactly what
+// raw byte equality gives against an ACGT-only query (align.cpp:134).
 template <int CS, int LANES>
 __device__ __forceinline__ void seg_stage_packed(const SegCtx<CS, LANES> &cx, const SeqSetDev &rset, const SeqSetDev &qset,
                                                  long long ref_off, int ref_len, long long query_off, int query_len,
@@ -226,17 +233,25 @@ __device__ __forceinline__ void seg_stage_packed(const SegCtx<CS, LANES> &cx, co
             if (x < rnw) cx.wr[x] = a;
             if (x < qnw) cx.wq[x] = b;
         }
+        if (rset.exc) {
+            const long long e0 = ref_off >> 5;
+            const int enw = (int)(((ref_off + ref_len - 1) >> 5) - e0) + 1;
+            for (int x = cx.sl; x < enw; x += LANES) cx.we[x] = __ldg(rset.exc + e0 + x);
+        }
     }
     __syncwarp();
     if (work) {
         const int ro = (int)(ref_off & 15), qo = (int)(query_off & 15);
         // DP index x (1-based) -> position in the staged words: natural order, or back to front for reverse tiles
         const int rbase = reverse ? ro + ref_len : ro - 1, qbase = reverse ? qo + query_len : qo - 1, step = reverse ? -1 : 1;
+        const int eo = (int)(ref_off & 31) - ro;             // bit position of a base in we[] = its position in wr[] + eo
+        const bool has_exc = rset.exc != nullptr;
         const int top = max(n + 1, m);
         for (int x = cx.sl; x <= top; x += LANES) {
             if (x >= 1 && x <= n + 1) {
-                const bool in = (x <= n);
                 const int pos = rbase + step * x;
+                bool in = (x <= n);
+                if (has_exc && in && ((cx.we[(pos + eo) >> 5] >> ((pos + eo) & 31)) & 1u)) in = false;
                 const uint32_t code = in ? (cx.wr[pos >> 4] >> (2 * (pos & 15))) & 3u : 0u;
                 cx.rb[x] = (uint16_t)(in ? enc_base((0x54474341u >> (8 * code)) & 0xffu) : SENT_R);
                 cx.rr[x] = in ? (cx.lut_mis ^ (cx.lut_delta << (8 * code))) : cx.lut_mis;
@@ -361,7 +376,7 @@ __device__ __forceinline__ int seg_dp(const SegCtx<CS, LANES> &cx, const uint32_
     // the loop stops at the corner step of each segment (at most two different ones per warp) so that the corner
     // value is picked out of the registers outside the loop
     for (int stop = kc_min;; stop = steps) {
-#pragma unroll (kTagUnroll)
+#pragma unroll (TagUnroll<CS, LANES>::value)
     for (; k <= stop; k++) {
         const uint32_t pack = __byte_perm(eG, eD, 0x7632);
         uint32_t recv = __shfl_up_sync(FULL, pack, 1, LANES);
@@ -614,8 +629,10 @@ gact_tile_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *_
         int n = d.ref_len, m = d.query_len;
         if (valid && d.first) { n = eff[t].n; m = eff[t].m; }
 
-        seg_stage<CS, LANES, LUT>(cx, P.sets[d.ref_set], P.sets[d.query_set], d.ref_off, d.ref_len, d.query_off,
-                                  d.query_len, d.reverse, n, m);
+        if constexpr (LUT) seg_stage_packed<CS, LANES>(cx, P.sets[d.ref_set], P.sets[d.query_set], d.ref_off, d.ref_len, d.query_off,
+                                                       d.query_len, d.reverse, n, m);
+        else seg_stage<CS, LANES, false>(cx, P.sets[d.ref_set], P.sets[d.query_set], d.ref_off, d.ref_len, d.query_off,
+                                         d.query_len, d.reverse, n, m);
         uint32_t q[CS];
         seg_load_q<CS, LANES, LUT>(cx, m, q);
         DirWinH<CS> dw;
@@ -674,8 +691,10 @@ gact_first_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *
         d.ref_off = 0; d.query_off = 0; d.ref_len = 0; d.query_len = 0; d.ref_set = 0; d.query_set = 0; d.reverse = 0; d.first = 0;
         if (valid) d = descs[t];
         const int n = d.ref_len, m = d.query_len;
-        seg_stage<CS, LANES, LUT>(cx, P.sets[d.ref_set], P.sets[d.query_set], d.ref_off, d.ref_len, d.query_off,
-                                  d.query_len, d.reverse, n, m);
+        if constexpr (LUT) seg_stage_packed<CS, LANES>(cx, P.sets[d.ref_set], P.sets[d.query_set], d.ref_off, d.ref_len, d.query_off,
+                                                       d.query_len, d.reverse, n, m);
+        else seg_stage<CS, LANES, false>(cx, P.sets[d.ref_set], P.sets[d.query_set], d.ref_off, d.ref_len, d.query_off,
+                                         d.query_len, d.reverse, n, m);
         uint32_t q[CS];
         seg_load_q<CS, LANES, LUT>(cx, m, q);
         int mi = 0, mj = 0;
@@ -1078,27 +1097,24 @@ inline void s16h_launch_chain(const S16HPlan &pl, KParams kp, const ChainCall *c
         grid < num_sms ? grid : num_sms);
 }
 
+// lut: score with the one-PRMT table from the packed words (tiles whose query window has no exception) or compare raw bytes
 inline void s16h_launch_first(const S16HPlan &pl, KParams kp, const gact_tile_desc *descs, const int *first_list,
-                              int n_first, EffLen *eff, int *counter, cudaStream_t st)
+                              int n_first, EffLen *eff, int *counter, cudaStream_t st, bool lut)
 {
     kp.s16_bias = pl.bias;
     kp.one = 1;
-    bool lut = pl.lut_ok;
-    for (int i = 0; i < GACT_MAX_SETS; i++) if (kp.sets[i].bytes) lut = false;
     s16h_pick_first(pl.CS, pl.lanes, lut)<<<s16h_grid(pl, n_first), pl.warps_per_cta * 32, pl.smem, st>>>(
         kp, descs, first_list, n_first, eff, counter, pl.seq_bytes);
 }
 
 inline void s16h_launch(const S16HPlan &pl, KParams kp, const gact_tile_desc *descs, const int *order, int n,
                         const EffLen *eff, gact_tile_result *results, uint32_t *states, int pitch_words, int *counter,
-                        cudaStream_t st, int scratch_region = 0)
+                        cudaStream_t st, int scratch_region, bool lut)
 {
     kp.win_rows = pl.win_rows;
     kp.win_lanes = pl.win_lanes;
     kp.s16_bias = pl.bias;
     kp.one = 1;
-    bool lut = pl.lut_ok;
-    for (int i = 0; i < GACT_MAX_SETS; i++) if (kp.sets[i].bytes) lut = false;
     s16h_pick(pl.CS, pl.lanes, lut)<<<s16h_grid(pl, n), pl.warps_per_cta * 32, pl.smem, st>>>(
         kp, descs, order, n, eff, results, states, pitch_words, counter, pl.seq_bytes,
         pl.d_scratch + (size_t)scratch_region * pl.scratch_bytes, pl.dir_bytes);

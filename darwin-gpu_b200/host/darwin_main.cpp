@@ -206,8 +206,12 @@ int main(int argc, char **argv)
             upload(GACT_SET_REF, ref.seqs, 0, ref.seqs.size());
             upload(GACT_SET_READS, reads.seqs, S.first_read, S.last_read);
             upload(GACT_SET_READS_RC, rev_reads, S.first_read, S.last_read);
+            bool slow_reads = false;                      // reads with bytes other than ACGT take the tile-by-tile path
+            for (size_t k = 0; k < S.last_read - S.first_read && !slow_reads; k++)
+                slow_reads = gact_engine_seq_has_exceptions(S.eng, GACT_SET_READS, (int64_t)k) == 1;
             if (use_chains && gact_engine_extend_supported(S.eng)) gact_engine_extend_reserve(S.eng, (int)(8 * (S.last_read - S.first_read) + 1024));
-            else gact_engine_reserve_tiles(S.eng);        // tile-by-tile host scheduler: its batch slots belong to initialisation
+            if (slow_reads || !(use_chains && gact_engine_extend_supported(S.eng)))
+                gact_engine_reserve_tiles(S.eng);         // tile-by-tile host scheduler: its batch slots belong to initialisation
             S.init_ms = ms_since(t_init);
         });
     }
@@ -337,8 +341,14 @@ int main(int argc, char **argv)
             per_batch = std::max<size_t>(per_batch, 1);
             const size_t B = std::max<size_t>(1, (nr + per_batch - 1) / per_batch);
             sh.batches = (int)B;
-            struct Batch { std::vector<GactCall> calls; std::vector<gact_call> gc; std::vector<gact_alignment> ga; };
+            // calls: every candidate of the batch in output order; gc: those that go through gact_engine_extend (gc_pos: their
+            // index in calls).  A candidate whose read holds a byte other than ACGT goes through the tile-by-tile host
+            // scheduler instead (raw-byte kernels), the reference's raw byte comparison needs that (align.cpp:134).
+            struct Batch { std::vector<GactCall> calls; std::vector<gact_call> gc; std::vector<size_t> gc_pos;
+                           std::vector<gact_alignment> ga, ga_dev; };
             std::vector<Batch> bt(B);
+            std::vector<GactCall> slow_calls;
+            std::vector<std::pair<size_t, size_t>> slow_at;           // (batch, index in calls)
             // candidates arrive grouped by query (= read, strand) in emission order, i.e. in the reference CPU build's
             // order per read: forward candidates, then reverse (darwin.cpp:209-288)
             for (int64_t i = 0; i < n_cands; i++) {
@@ -350,15 +360,22 @@ int main(int argc, char **argv)
                 ref_pos -= (int)(chr_start_bin[chr] * cfg.bin_size);
                 if (ref_pos > (long long)ref.seqs[chr].size()) ref_pos = (int)ref.seqs[chr].size();       // darwin.cpp:222-224
                 (comp ? sh.cand_rev : sh.cand_fwd)++;
-                Batch &x = bt[std::min(B - 1, local / per_batch)];
+                const size_t bi = std::min(B - 1, local / per_batch);
+                Batch &x = bt[bi];
                 x.calls.push_back(GactCall{chr, (int32_t)local, ref_pos, (int)c.offset, (uint8_t)(comp ? 1 : 0)});
+                if (gact_engine_seq_has_exceptions(eng, GACT_SET_READS, (int64_t)local) == 1) {
+                    slow_calls.push_back(x.calls.back());
+                    slow_at.emplace_back(bi, x.calls.size() - 1);
+                    continue;
+                }
                 gact_call g;
                 memset(&g, 0, sizeof(g));
                 g.ref_seq = chr; g.query_seq = (int32_t)local; g.ref_pos = ref_pos; g.query_pos = (int)c.offset;
                 g.query_set = comp ? GACT_SET_READS_RC : GACT_SET_READS;
                 x.gc.push_back(g);
+                x.gc_pos.push_back(x.calls.size() - 1);
             }
-            for (Batch &x : bt) x.ga.resize(x.gc.size());
+            for (Batch &x : bt) { x.ga.resize(x.calls.size()); x.ga_dev.resize(x.gc.size()); }
             sh.text.assign(B, std::string());
             sh.dsoft_ms = ms_since(td);
             {
@@ -367,6 +384,25 @@ int main(int argc, char **argv)
                 std::cout << "Time finding seeds: " << sh.dsoft_ms << " msec" << std::endl;
             }
             const auto tg = Clock::now();
+            if (!slow_calls.empty()) {
+                // reads with exceptions: tile by tile through the host scheduler, before the chain batches are in flight
+                std::vector<SeqView> rd(nr), rc_views(nr);
+                for (size_t k = 0; k < nr; k++) {
+                    rd[k] = SeqView{reads.seqs[sh.first_read + k].data(), (int64_t)reads.seqs[sh.first_read + k].size()};
+                    rc_views[k] = SeqView{rev_reads[sh.first_read + k].data(), (int64_t)rev_reads[sh.first_read + k].size()};
+                }
+                std::vector<GactAlignment> slow_aln;
+                GactScheduler sched(eng, gp, ref_views, rd, rc_views, sh.dsoft_threads);
+                sched.run(slow_calls, slow_aln, &sh.stats);
+                for (size_t k = 0; k < slow_calls.size(); k++) {
+                    const GactAlignment &a = slow_aln[k];
+                    gact_alignment g;
+                    memset(&g, 0, sizeof(g));
+                    g.ab = a.ab; g.ae = a.ae; g.bb = a.bb; g.be = a.be; g.score = a.score; g.first_tile_score = a.first_tile_score;
+                    g.n_tiles = a.n_tiles; g.n_cells = a.n_cells;
+                    bt[slow_at[k].first].ga[slow_at[k].second] = g;
+                }
+            }
 
             // writer thread: batches in order, same line order as the sequential loop of the reference
             std::mutex wm;
@@ -405,10 +441,14 @@ int main(int argc, char **argv)
             };
             auto extend_collect = [&](size_t b) -> int {
                 const auto tw = Clock::now();
-                const int r = gact_engine_extend_wait(eng, bt[b].ga.data());
+                const int r = gact_engine_extend_wait(eng, bt[b].ga_dev.data());
                 sh.extend_wait_us += us_since(tw);
                 if (r) return r;
-                for (const gact_alignment &a : bt[b].ga) { sh.stats.tiles += (uint64_t)a.n_tiles; sh.stats.cells += (uint64_t)a.n_cells; }
+                for (size_t k = 0; k < bt[b].ga_dev.size(); k++) {
+                    const gact_alignment &a = bt[b].ga_dev[k];
+                    bt[b].ga[bt[b].gc_pos[k]] = a;
+                    sh.stats.tiles += (uint64_t)a.n_tiles; sh.stats.cells += (uint64_t)a.n_cells;
+                }
                 { std::lock_guard<std::mutex> lk(wm); ready = b + 1; }
                 wcv.notify_all();
                 return GACT_OK;

@@ -49,7 +49,7 @@ class GactError(RuntimeError):
 EXPORTS = [
     "gact_abi_version", "gact_status_string", "gact_device_count", "gact_engine_create",
     "gact_engine_destroy", "gact_last_error", "gact_engine_upload", "gact_engine_seq_start",
-    "gact_engine_set_length", "gact_engine_set_bits", "gact_engine_states_pitch_words",
+    "gact_engine_set_length", "gact_engine_set_bits", "gact_engine_seq_has_exceptions", "gact_engine_states_pitch_words",
     "gact_engine_max_tiles", "gact_engine_align_tiles", "gact_engine_submit", "gact_engine_wait", "gact_engine_wait_view",
     "gact_engine_stage", "gact_engine_run_staged", "gact_engine_fetch_staged", "gact_engine_sync",
     "gact_engine_last_kernel_ms", "gact_engine_stats", "gact_engine_reset_stats",
@@ -98,6 +98,8 @@ def load():
     L.gact_engine_set_length.argtypes = [vp, i32]
     L.gact_engine_set_bits.restype = i32
     L.gact_engine_set_bits.argtypes = [vp, i32]
+    L.gact_engine_seq_has_exceptions.restype = i32
+    L.gact_engine_seq_has_exceptions.argtypes = [vp, i32, i64]
     L.gact_engine_states_pitch_words.restype = i32
     L.gact_engine_states_pitch_words.argtypes = [vp]
     L.gact_engine_max_tiles.restype = i32
@@ -241,6 +243,9 @@ class GactEngine:
 
     def set_bits(self, set_id):
         return self.L.gact_engine_set_bits(self.h, set_id)
+
+    def seq_has_exceptions(self, set_id, i):
+        return self.L.gact_engine_seq_has_exceptions(self.h, set_id, i)
 
     def set_kernel(self, variant):
         self._ck(self.L.gact_engine_set_kernel(self.h, variant), "gact_engine_set_kernel")

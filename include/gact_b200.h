@@ -150,18 +150,26 @@ void gact_engine_destroy(gact_engine *e);
 const char *gact_last_error(const gact_engine *e);  /* e may be NULL: last create error */
 
 /* Upload one sequence set: n_seqs byte strings (raw FASTA characters, no
- * terminator needed), concatenated on the device in order.  Sets made only of
- * 'A','C','G','T' are kept 2-bit packed (16 bases per 32-bit word); anything
- * else keeps 8 bits per base so that the reference's raw byte comparison
- * (align.cpp:134: 'N'=='N', 'a'!='A') is preserved.  Replaces a previous
- * upload of the same set. */
+ * terminator needed), concatenated on the device in order.  Every set is kept
+ * 2-bit packed (16 bases per 32-bit word; case folded, anything else 0 --
+ * ntcoding.cpp:60-72, what D-SOFT hashes).  A set that holds any byte other
+ * than 'A','C','G','T' (an "exception": N, lower case, IUPAC codes) also keeps
+ * an exception bitmap and its raw bytes, so that the reference's raw byte
+ * comparison (align.cpp:134: 'N'=='N', 'a'!='A') is preserved exactly: tiles
+ * whose QUERY window holds an exception are aligned by the byte-comparing
+ * kernels, all others (exceptions in the reference window included) by the
+ * packed score-table kernels; the engine routes every tile of a batch itself.
+ * Replaces a previous upload of the same set. */
 int gact_engine_upload(gact_engine *e, int set, int64_t n_seqs,
                        const char *const *seqs, const int64_t *lens);
 /* Offset of sequence i inside its set (what to add to a position to form
  * gact_tile_desc.ref_off / query_off). */
 int64_t gact_engine_seq_start(const gact_engine *e, int set, int64_t i);
 int64_t gact_engine_set_length(const gact_engine *e, int set);
-int     gact_engine_set_bits(const gact_engine *e, int set);   /* 2, 8 or 0 (empty) */
+int     gact_engine_set_bits(const gact_engine *e, int set);   /* 2: ACGT only, 8: raw bytes kept too, 0: empty */
+/* 1 if sequence i of the set holds a byte other than ACGT, 0 if not, <0 on bad arguments.  Such a sequence cannot be
+ * the QUERY of gact_engine_extend (its candidates go through the tile path); as a reference it can. */
+int     gact_engine_seq_has_exceptions(const gact_engine *e, int set, int64_t i);
 
 int gact_engine_states_pitch_words(const gact_engine *e);
 int gact_engine_max_tiles(const gact_engine *e);
@@ -213,9 +221,10 @@ int gact_engine_get_kernel(const gact_engine *e);
 /* ---- whole candidate extensions on the device (GACT(), gact.cpp:48-228) ----
  * One call = one D-SOFT candidate: left extension, right extension from the first tile's maximum,
  * first-tile threshold, total score -- the tile chain is walked on the GPU, the host gets one
- * gact_alignment per call and no traceback states.  Supported when the packed s16x2 kernels can run the
- * engine's parameters (any tile_size <= GACT_MAX_TILE_SIZE with scores in the 16-bit range) and the sets in use
- * hold only ACGT; otherwise GACT_ERR_ARG is returned and the caller drives tiles itself
+ * gact_alignment per call and no traceback states.  Supported when the packed s16x2 score-table kernels can run the
+ * engine's parameters (any tile_size <= GACT_MAX_TILE_SIZE with scores in the 16-bit range, |16 * score| < 128).
+ * Bytes other than ACGT in the reference are handled; a call whose QUERY sequence holds one
+ * (gact_engine_seq_has_exceptions) is refused with GACT_ERR_ARG -- the caller drives that candidate's tiles itself
  * (gact_engine_submit/wait, as host/gact_scheduler.cpp does). */
 typedef struct {
     int32_t ref_seq;      /* sequence index inside GACT_SET_REF                    */

@@ -135,11 +135,37 @@ def test_extend_async_batches_match_sync(pygact):
         assert len(eng.extend_wait()) == 0
 
 
-def test_extend_refuses_non_acgt_sets(pygact):
-    G = pygact
-    with G.GactEngine(max_tiles=16) as eng:
-        eng.upload(G.SET_REF, [b"ACGTNACGT" * 50])
-        eng.upload(G.SET_READS, [b"ACGT" * 50])
-        assert not eng.extend_supported()
-        with pytest.raises(G.GactError):
-            eng.extend(np.zeros(1, dtype=G.CALL_DTYPE))
+def test_extend_with_exceptions_in_the_reference(pygact, oracle):
+    """N runs / lower case in the REFERENCE stay on the device chains (an exception row mismatches every ACGT query base,
+    which is what raw byte equality gives); a QUERY sequence with such a byte is refused, per sequence."""
+    G, O = pygact, oracle
+    genome, reads, rc, calls = make_case(11, n_reads=14)
+    rng = np.random.default_rng(3)
+    g0 = genome[0].copy()
+    for _ in range(40):                                    # N runs and lower-case stretches
+        p = int(rng.integers(0, len(g0) - 400))
+        L = int(rng.integers(1, 300))
+        if rng.random() < 0.5:
+            g0[p:p + L] = ord("N")
+        else:
+            g0[p:p + L] |= 0x20
+    idx = rng.integers(0, len(g0), size=len(g0) // 50)
+    g0[idx] = np.frombuffer(b"NnRY", dtype=np.uint8)[rng.integers(0, 4, size=len(idx))]
+    genome = [g0, genome[1]]
+    dirty = bytearray(reads[0]); dirty[len(dirty) // 2] = ord("N")
+    reads2, rc2 = reads + [bytes(dirty)], rc + [bytes(dirty[::-1])]
+    for mode in (0, 1, 3):
+        with G.GactEngine(first_tile_score_threshold=35, max_tiles=64) as eng:
+            eng.upload(G.SET_REF, [g.tobytes() for g in genome])
+            eng.upload(G.SET_READS, reads2)
+            eng.upload(G.SET_READS_RC, rc2)
+            assert eng.set_bits(G.SET_REF) == 8 and eng.set_bits(G.SET_READS) == 8
+            assert eng.extend_supported()
+            assert eng.seq_has_exceptions(G.SET_READS, len(reads2) - 1) == 1 and eng.seq_has_exceptions(G.SET_READS, 0) == 0
+            assert eng.seq_has_exceptions(G.SET_REF, 0) == 1 and eng.seq_has_exceptions(G.SET_REF, 1) == 0
+            eng.set_chain_mode(mode)
+            out = eng.extend(_calls_array(G, calls))
+            with pytest.raises(G.GactError):
+                eng.extend(_calls_array(G, [(0, len(reads2) - 1, 100, 100, 1)]))
+        assert _check_against_oracle(O, genome, reads, rc, calls, out, 320, 120, (1, -1, -1, -1)) == len(calls)
+    assert (out["score"] > 300).sum() > 5

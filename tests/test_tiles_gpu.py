@@ -131,6 +131,41 @@ def test_raw_byte_semantics_8bit_sets(pygact, oracle, variant):
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("where", ["ref", "query_some", "both_some"])
+def test_exceptions_routed_per_tile(pygact, oracle, variant, where):
+    """Bytes other than ACGT in the reference only (score-table kernels with sentinel rows), in some query windows (those
+    tiles go to the raw-byte kernels, the rest of the batch stays on the table kernels) or in both: raw byte equality
+    (align.cpp:134) on every tile."""
+    G, O = pygact, oracle
+    import synth
+    mb = synth.tile_microbatch(1500, seed=31, first_frac=0.25)
+    rng = np.random.default_rng(5)
+    ref, qry = mb["ref"].copy(), mb["query"].copy()
+    sub = np.frombuffer(b"NNNacgtnRY", dtype=np.uint8)
+
+    def sprinkle(buf, frac, runs):
+        idx = rng.integers(0, len(buf), size=int(len(buf) * frac))
+        buf[idx] = sub[rng.integers(0, len(sub), size=len(idx))]
+        for _ in range(runs):
+            p = int(rng.integers(0, len(buf) - 200))
+            buf[p:p + int(rng.integers(1, 150))] = ord("N")
+
+    if where in ("ref", "both_some"):
+        sprinkle(ref, 0.01, 30)
+    if where in ("query_some", "both_some"):
+        sprinkle(qry[: len(qry) // 3], 0.002, 10)        # only the first third of the query buffer: most windows stay clean
+    mb["ref"], mb["query"] = ref, qry
+    with _engine(G, variant, max_tiles=1500) as eng:
+        eng.upload(G.SET_REF, [ref.tobytes()])
+        eng.upload(G.SET_READS, [qry.tobytes()])
+        assert eng.set_bits(G.SET_REF) == (8 if where != "query_some" else 2)
+        res, st = eng.align_tiles(engine_descs(G, mb))
+    ores, ost = O.align_batch(ref, qry, oracle_descs(O, mb), n_threads=8)
+    bad = compare_batch(res, st, ores, ost)
+    assert len(bad) == 0, f"{len(bad)} tiles differ, first {bad[:5]}"
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_empty_and_tiny_tiles(pygact, variant):
     G = pygact
     with _engine(G, variant, max_tiles=16) as eng:
