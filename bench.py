@@ -62,6 +62,10 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reads-leg", action="store_true", help="skip the application-level reads/s leg")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 1, 5],
+                    help="run one of the other BASELINE.json configs at size instead of the bench line: 1 = de-novo self-alignment "
+                         "of a 10x read set of a 4.64 Mbp genome, 5 = tile-size sweep 256/512/1024 on 30 kb reads")
+    ap.add_argument("--cpu-reads", type=int, default=100, help="--config: reads given to the reference CPU build")
     return ap.parse_args()
 
 
@@ -333,6 +337,84 @@ def reads_leg(n_gpus, cpu_arm_reads=200):
         shutil.rmtree(wd, ignore_errors=True)
 
 
+PARAMS_TMPL = None
+
+
+def params_cfg(tile=None, overlap=None):
+    """params.cfg defaults of the package, optionally with another tile_size / tile_overlap."""
+    import re
+    txt = open(os.path.join(ROOT, "darwin-gpu_b200", "params.cfg")).read()
+    if tile is not None:
+        txt = re.sub(r"(?m)^tile_size\s*=.*$", f"tile_size = {tile}", txt)
+        txt = re.sub(r"(?m)^tile_overlap\s*=.*$", f"tile_overlap = {overlap}", txt)
+    return txt
+
+
+def config_at_size(which, n_gpus, cpu_reads):
+    """BASELINE.json configs 1 and 5 at their named sizes: one JSON record per run, the reference CPU build on
+    a `cpu_reads`-read subset with its sorted|uniq output compared with ours, line count + md5 of our full output."""
+    import hashlib
+    import re
+    import shutil
+    import tempfile
+    import synth
+    exe = os.path.join(ROOT, "darwin-gpu_b200", "darwin")
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "darwin_ref")
+    cores = usable_cores()
+    wd = tempfile.mkdtemp(prefix=f"bench_config{which}_")
+    out = {"config": which, "gpus": n_gpus, "host_threads": cores, "runs": []}
+    try:
+        if which == 1:
+            # README:25 stand-in: 4 641 652 bp genome (seed 1), PBSIM-CLR-like reads to 10x, self-aligned, params.cfg defaults
+            genome = [synth.random_genome(4_641_652, np.random.default_rng(1))]
+            names, reads = synth.sample_reads(genome, 46_416_520, np.random.default_rng(2), mean=3000, sd=2300, lo=100, hi=25000)
+            synth.write_fasta(os.path.join(wd, "reads.fasta"), names, reads)
+            jobs = [("self-alignment", "reads.fasta", "reads.fasta", None, None)]
+            out["workload"] = (f"config 1: {len(reads)} PBSIM-CLR-like reads ({sum(len(r) for r in reads)} bases = 10x of a 4 641 652 bp "
+                               "genome, 15 % error), reads.fasta against itself, params.cfg defaults")
+        else:
+            rng = np.random.default_rng(3)
+            genome = [synth.random_genome(5_000_000, rng) for _ in range(20)]
+            synth.write_fasta(os.path.join(wd, "ref.fasta"), [f"chr{i}" for i in range(20)], genome)
+            names, reads = synth.sample_reads(genome, 51_000_000, np.random.default_rng(5), mean=30000, sd=3000, lo=20000, hi=40000)
+            synth.write_fasta(os.path.join(wd, "reads.fasta"), names, reads)
+            jobs = [(f"tile_size {t} / overlap {o}", "ref.fasta", "reads.fasta", t, o) for t, o in ((256, 96), (512, 192), (1024, 384))]
+            out["workload"] = (f"config 5: {len(reads)} ultra-long reads (~30 kb, {sum(len(r) for r in reads)} bases, 15 % error) vs the "
+                               "100 Mbp config-3 reference, tile_size 256/512/1024 with tile_overlap = 0.375 tile_size")
+        n_sub = min(cpu_reads, len(reads))
+        synth.write_fasta(os.path.join(wd, "reads_sub.fasta"), names[:n_sub], reads[:n_sub])
+        sub_names = set(names[:n_sub])
+        for label, ref_file, reads_file, tile, overlap in jobs:
+            open(os.path.join(wd, "params.cfg"), "w").write(params_cfg(tile, overlap))
+            stdout, lines, wall = _run_darwin(exe, wd, ref_file, reads_file, cores, env={"DARWIN_GPUS": str(n_gpus)})
+            summ = json.loads(re.search(r"DARWIN_B200_SUMMARY (\{.*\})", stdout).group(1))
+            uniq = sorted(set(lines))
+            align_s = max(summ["align_phase_ms"], 1e-3) / 1e3
+            rec = {"run": label, "reads": len(reads), "reads_per_s": len(reads) / align_s, "align_phase_ms": summ["align_phase_ms"],
+                   "wall_s": wall, "tiles": summ["tiles"], "cells": summ["cells"], "gcups_align_phase": summ["cells"] / align_s / 1e9,
+                   "candidates": summ["candidates"], "unique_overlap_lines": len(uniq),
+                   "md5_sorted_uniq": hashlib.md5("\n".join(uniq).encode()).hexdigest()}
+            if os.path.exists(ref_exe):
+                # same inputs for both builds: the subset as reads against the run's reference file (for config 1 the full
+                # read set, i.e. a reads-vs-reference run of the subset -- the self-alignment of the whole set would take
+                # the CPU build hours)
+                so, sl, sw = _run_darwin(exe, wd, ref_file, "reads_sub.fasta", cores, env={"DARWIN_GPUS": str(n_gpus)})
+                ours_sub = sorted(set(sl))
+                ro, rl, rw = _run_darwin(ref_exe, wd, ref_file, "reads_sub.fasta", cores, timeout=3000)
+                m = re.search(r"Time elapsed \(seed table querying \+ aligning\): (\d+) msec", ro)
+                ref_align_s = max(int(m.group(1)), 1) / 1e3
+                ssum = json.loads(re.search(r"DARWIN_B200_SUMMARY (\{.*\})", so).group(1))
+                rec["subset"] = {"reads": n_sub, "reference_cpu_align_phase_ms": ref_align_s * 1e3,
+                                 "reference_cpu_reads_per_s": n_sub / ref_align_s, "reference_cpu_wall_s": rw,
+                                 "ours_align_phase_ms": ssum["align_phase_ms"], "unique_overlap_lines": len(ours_sub),
+                                 "sorted_uniq_identical": bool(sorted(set(rl)) == ours_sub)}
+                rec["reads_per_s_vs_reference_cpu"] = rec["reads_per_s"] / rec["subset"]["reference_cpu_reads_per_s"]
+            out["runs"].append(rec)
+        return out
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+
+
 def gpu_baseline_leg(n_tiles=1 << 16):
     """The reference's own GPU kernel on the same box (tools/ref_gpu_bench.py in a subprocess)."""
     try:
@@ -371,6 +453,9 @@ def main():
     args = parse()
     if args.impl == "reference":
         return reference_main(args)
+    if args.config:
+        print(json.dumps(config_at_size(args.config, args.gpus, args.cpu_reads)))
+        return
 
     import torch
     import pygact as G
