@@ -14,6 +14,10 @@
 //                        engine supports it; 0: tile-by-tile host scheduler (GactScheduler)
 //   DARWIN_DSOFT=<gpu|host> where the D-SOFT filter runs (default gpu: gact_dsoft_run on the shard's GPU;
 //                        host: SeedTable::dsoft on CPU_THREADS / n host threads)
+//   DARWIN_MULTIPROC=<1|0> with more than one GPU: 1 (default) one worker PROCESS per GPU -- CUDA driver start-up and context
+//                        creation are serialised inside a process (about 0.4 s per GPU) but run in parallel across processes,
+//                        so the whole-program wall time no longer grows with the GPU count; 0: one host thread per GPU in
+//                        this process (the reference's model, darwin.cpp:619-629).  Same files, same bracket, same output.
 //   DARWIN_BATCH_READS=<n> reads per pipeline batch of a shard (default: auto, about 1 200; 0 = one batch): D-SOFT of
 //                        batch k+1 and the output of batch k-1 overlap the alignment chains of batch k
 //   DARWIN_SORTED_OUT=<file> additionally write the sorted, duplicate-free union of all darwin.<tid>.out lines
@@ -38,6 +42,12 @@
 #include <condition_variable>
 #include <thread>
 #include <vector>
+
+#include <fcntl.h>
+#include <poll.h>
+#include <sys/types.h>
+#include <sys/wait.h>
+#include <unistd.h>
 
 #include "../../include/gact_b200.h"
 #include "darwin_config.h"
@@ -77,6 +87,190 @@ struct Shard {
     double table_kernel_ms = 0.0;
 };
 
+// Lines that belong to one shard ("num_candidates: F R", "Time finding seeds", ...).  A worker process keeps its general
+// chatter to itself (stdout -> /dev/null) and writes only these, whole lines at a time, to the real stdout.
+static int g_shard_fd = -1;
+static void shard_print(const std::string &line)
+{
+    std::lock_guard<std::mutex> lk(io_lock);
+    if (g_shard_fd >= 0) {
+        const std::string l = line + "\n";
+        ssize_t r = write(g_shard_fd, l.data(), l.size());
+        (void)r;
+    } else {
+        std::cout << line << std::endl;
+    }
+}
+
+// One worker process per GPU (DARWIN_MULTIPROC): the coordinator side.  Workers are this binary again with
+// DARWIN_WORKER="<index> <count>"; fd 3 carries the "go" byte to the worker, fd 4 its READY / DONE lines back.
+struct WorkerProc {
+    pid_t pid = -1;
+    int ctl = -1, rep = -1;          // coordinator's ends
+    std::string buf, ready, done;    // JSON payloads of the READY / DONE lines
+    bool eof = false;
+};
+
+static double json_num(const std::string &js, const std::string &key, double dflt = 0.0)
+{
+    const std::string k = "\"" + key + "\": ";
+    const size_t p = js.find(k);
+    if (p == std::string::npos) return dflt;
+    return atof(js.c_str() + p + k.size());
+}
+
+static int coordinate(int argc, char **argv, int G, const Params &cfg, int num_threads, bool same_file)
+{
+    const auto t_prog = Clock::now();
+    std::vector<std::pair<std::string, double>> timeline;
+    auto mark = [&](const char *what) { timeline.emplace_back(what, us_since(t_prog) / 1e3); };
+    printf("CPU threads: %d\n", num_threads);
+    printf("Scores: match = %d, mismatch = %d, gap_open = %d, gap_extend = %d\n", cfg.match, cfg.mismatch, cfg.gap_open, cfg.gap_extend);
+    printf("Minimizer window size: %d\n", (int)cfg.window_size);
+    printf("Using GPU: %d device(s), one worker process per device\n", G);
+    fflush(stdout);
+    std::vector<WorkerProc> w((size_t)G);
+    for (int g = 0; g < G; g++) {
+        int c2w[2], w2c[2];
+        if (pipe2(c2w, O_CLOEXEC) || pipe2(w2c, O_CLOEXEC)) { perror("pipe2"); return 3; }
+        const pid_t pid = fork();
+        if (pid < 0) { perror("fork"); return 3; }
+        if (pid == 0) {
+            // keep clear of the fds we are about to overwrite
+            const int rd = fcntl(c2w[0], F_DUPFD, 10), wr = fcntl(w2c[1], F_DUPFD, 10);
+            dup2(rd, 3);
+            dup2(wr, 4);
+            const std::string env = std::to_string(g) + " " + std::to_string(G);
+            setenv("DARWIN_WORKER", env.c_str(), 1);
+            execv("/proc/self/exe", argv);
+            perror("execv");
+            _exit(127);
+        }
+        close(c2w[0]); close(w2c[1]);
+        w[(size_t)g].pid = pid; w[(size_t)g].ctl = c2w[1]; w[(size_t)g].rep = w2c[0];
+    }
+    mark("workers_spawned");
+    // read lines from every worker until `want` of them have delivered the given kind of line
+    auto pump = [&](bool want_done) -> bool {
+        for (;;) {
+            size_t have = 0;
+            for (auto &x : w) have += want_done ? !x.done.empty() : !x.ready.empty();
+            if (have == w.size()) return true;
+            std::vector<pollfd> pf;
+            for (auto &x : w) if (!x.eof) pf.push_back(pollfd{x.rep, POLLIN, 0});
+            if (pf.empty()) return false;
+            if (poll(pf.data(), pf.size(), -1) < 0) { if (errno == EINTR) continue; return false; }
+            for (auto &x : w) {
+                if (x.eof) continue;
+                for (auto &q : pf) if (q.fd == x.rep && (q.revents & (POLLIN | POLLHUP))) {
+                    char tmp[4096];
+                    const ssize_t r = read(x.rep, tmp, sizeof(tmp));
+                    if (r <= 0) { x.eof = true; break; }
+                    x.buf.append(tmp, (size_t)r);
+                    size_t nl;
+                    while ((nl = x.buf.find('\n')) != std::string::npos) {
+                        const std::string line = x.buf.substr(0, nl);
+                        x.buf.erase(0, nl + 1);
+                        if (line.compare(0, 6, "READY ") == 0) x.ready = line.substr(6);
+                        else if (line.compare(0, 5, "DONE ") == 0) x.done = line.substr(5);
+                    }
+                }
+                if (x.eof && (want_done ? x.done.empty() : x.ready.empty())) return false;     // died before reporting
+            }
+        }
+    };
+    auto fail_all = [&](const char *what) {
+        fprintf(stderr, "darwin: %s\n", what);
+        for (auto &x : w) if (x.pid > 0) kill(x.pid, SIGTERM);
+        for (auto &x : w) if (x.pid > 0) waitpid(x.pid, nullptr, 0);
+        return 3;
+    };
+    if (!pump(false)) return fail_all("a worker process ended before it was ready (see its messages above)");
+    mark("workers_ready_bracket_opens");
+    const std::string &r0 = w[0].ready;
+    std::cout << "\nLoading reference genome ...\nReference length: " << (long long)json_num(r0, "reference_length") << ", "
+              << (int)json_num(r0, "ref_pieces") << " pieces\nTime elapsed (loading reference genome): "
+              << (long)json_num(r0, "load_ref_ms") << " msec\n\nLoading reads ...\nNumber of reads: " << (long long)json_num(r0, "reads")
+              << "\nTime elapsed (loading reads): " << (long)json_num(r0, "load_reads_ms") << " msec\n";
+    double init_ms = 0, table_ms = 0, setup_ms = 0;
+    for (int g = 0; g < G; g++) {
+        init_ms = std::max(init_ms, json_num(w[(size_t)g].ready, "gpu_init_ms"));
+        table_ms = std::max(table_ms, json_num(w[(size_t)g].ready, "seed_table_phase_ms"));
+        setup_ms = std::max(setup_ms, json_num(w[(size_t)g].ready, "worker_setup_ms"));
+        std::cout << "GPU " << g << " worker: CUDA up after " << (long)json_num(w[(size_t)g].ready, "cuda_up_ms") << " msec, init (context, engine, "
+                  << "sequence upload) " << (long)json_num(w[(size_t)g].ready, "gpu_init_ms") << " msec, seed table build (H2D + kernels) "
+                  << json_num(w[(size_t)g].ready, "seed_table_ms") << " msec, ready after " << (long)json_num(w[(size_t)g].ready, "ready_ms") << " msec\n";
+    }
+    std::cout << "Time elapsed (GPU init): " << (long)init_ms << " msec\nTime elapsed (seed position table construction): " << (long)table_ms
+              << " msec\n\nFinding candidate bin locations for each read: \n" << G << " threads created\nSynchronizing all threads...\n" << std::flush;
+    // ---- the timed bracket: from "every worker is ready" to "every worker has written its output" ----
+    const auto t0 = Clock::now();
+    for (auto &x : w) { const char go = 'G'; ssize_t r = write(x.ctl, &go, 1); (void)r; }
+    if (!pump(true)) return fail_all("a worker process ended before it finished its shard");
+    const double align_us = us_since(t0);
+    mark("bracket_closes");
+    std::cout << "Time elapsed (seed table querying + aligning): " << (long)(align_us / 1e3 + 0.5) << " msec" << std::endl;
+    printf("Time elapsed (worker set-up before the bracket: thread start, device binding, output file creation): %.3f msec\n", setup_ms);
+    int rcode = 0;
+    for (auto &x : w) {
+        int st = 0;
+        waitpid(x.pid, &st, 0);
+        if (!(WIFEXITED(st) && WEXITSTATUS(st) == 0)) rcode = 3;
+        close(x.ctl); close(x.rep);
+    }
+    mark("workers_exited");
+    long sorted_ms = -1;
+    size_t sorted_lines = 0;
+    if (const char *sp = getenv("DARWIN_SORTED_OUT")) {
+        const auto ts = Clock::now();
+        std::vector<std::string> lines;
+        for (int g = 0; g < G; g++) {
+            std::ifstream in("darwin." + std::to_string(g) + ".out");
+            std::string ln;
+            while (std::getline(in, ln)) lines.push_back(ln);
+        }
+        std::sort(lines.begin(), lines.end());
+        lines.erase(std::unique(lines.begin(), lines.end()), lines.end());
+        std::ofstream so(sp);
+        for (auto &ln : lines) so << ln << '\n';
+        so.close();
+        sorted_lines = lines.size();
+        sorted_ms = ms_since(ts);
+        std::cout << "Time elapsed (sorted unique overlap file, " << sorted_lines << " lines): " << sorted_ms << " msec" << std::endl;
+    }
+    const double wall_s = std::chrono::duration<double>(Clock::now() - t_prog).count();
+    std::cout << "Time elapsed (program start to here): " << (long)(wall_s * 1e3 + 0.5) << " msec" << std::endl;
+    unsigned long long tiles = 0, cells = 0, cand = 0;
+    double dev_ms = 0, sched_ms = 0;
+    int batches = 0;
+    for (auto &x : w) {
+        tiles += (unsigned long long)json_num(x.done, "tiles"); cells += (unsigned long long)json_num(x.done, "cells");
+        cand += (unsigned long long)json_num(x.done, "candidates");
+        dev_ms = std::max(dev_ms, json_num(x.done, "gact_kernel_ms"));
+        sched_ms = std::max(sched_ms, json_num(x.done, "gact_sched_ms"));
+        batches = std::max(batches, (int)json_num(x.done, "chain_batches"));
+        if (json_num(x.done, "error") != 0) rcode = 3;
+    }
+    {
+        std::string tl = "DARWIN_B200_TIMELINE {";
+        for (size_t i = 0; i < timeline.size(); i++) {
+            char buf[160];
+            snprintf(buf, sizeof(buf), "%s\"%s\": %.1f", i ? ", " : "", timeline[i].first.c_str(), timeline[i].second);
+            tl += buf;
+        }
+        tl += "}";
+        puts(tl.c_str());
+    }
+    printf("DARWIN_B200_SUMMARY {\"reads\": %lld, \"gpus\": %d, \"candidates\": %llu, \"tiles\": %llu, \"cells\": %llu, "
+           "\"align_phase_ms\": %.3f, \"worker_setup_ms\": %.3f, \"gact_sched_ms\": %.1f, \"gact_kernel_ms\": %.1f, "
+           "\"gpu_init_ms\": %.0f, \"seed_table_ms\": %.1f, \"teardown_ms\": %ld, \"chain_batches\": %d, \"wall_s\": %.3f, "
+           "\"sorted_unique_lines\": %zu, \"worker_processes\": %d}\n",
+           (long long)json_num(r0, "reads"), G, cand, tiles, cells, align_us / 1e3, setup_ms, sched_ms, dev_ms, init_ms, table_ms, 0L, batches,
+           wall_s, sorted_lines, G);
+    (void)same_file; (void)argc;
+    return rcode;
+}
+
 int main(int argc, char **argv)
 {
     if (argc < 4) {
@@ -91,8 +285,31 @@ int main(int argc, char **argv)
         return 1;
     }
     const std::string ref_path(argv[1]), reads_path(argv[2]);
-    const int num_threads = std::max(1, atoi(argv[3]));
+    int num_threads = std::max(1, atoi(argv[3]));
     const bool same_file = (ref_path == reads_path);            // darwin.cpp:498-503
+    // worker process of a multi-GPU run (see coordinate()): shard wk_index of wk_count, fd 3 = "go", fd 4 = reports
+    int wk_index = -1, wk_count = 0;
+    if (const char *wenv = getenv("DARWIN_WORKER")) {
+        if (sscanf(wenv, "%d %d", &wk_index, &wk_count) != 2 || wk_index < 0 || wk_index >= wk_count) {
+            fprintf(stderr, "darwin: bad DARWIN_WORKER\n");
+            return 1;
+        }
+        unsetenv("DARWIN_WORKER");
+        g_shard_fd = dup(1);
+        if (!freopen("/dev/null", "w", stdout)) return 1;
+        num_threads = std::max(1, num_threads / wk_count);
+    }
+    const bool is_worker = wk_index >= 0;
+    auto report = [&](const std::string &line) {               // worker -> coordinator
+        const std::string l = line + "\n";
+        ssize_t r = write(4, l.data(), l.size());
+        (void)r;
+    };
+    if (!is_worker && getenv("DARWIN_GPUS") && atoi(getenv("DARWIN_GPUS")) > 1 &&
+        !(getenv("DARWIN_MULTIPROC") && atoi(getenv("DARWIN_MULTIPROC")) == 0)) {
+        printf("same_file: %d\n", same_file ? 1 : 0);
+        return coordinate(argc, argv, atoi(getenv("DARWIN_GPUS")), cfg, num_threads, same_file);
+    }
     printf("same_file: %d\n", same_file ? 1 : 0);
 
     // the device query initialises the CUDA driver (hundreds of ms): run it beside the FASTA loading
@@ -140,7 +357,8 @@ int main(int argc, char **argv)
     }
     const uint32_t reference_length = (uint32_t)ref_string.size();
     std::cout << "Reference length: " << reference_length << ", " << ref.seqs.size() << " pieces" << std::endl;
-    std::cout << "Time elapsed (loading reference genome): " << ms_since(t0) << " msec" << std::endl;
+    const long load_ref_ms = ms_since(t0);
+    std::cout << "Time elapsed (loading reference genome): " << load_ref_ms << " msec" << std::endl;
 
     // ---- reads ----------------------------------------------------------------------------
     std::cout << "\nLoading reads ...\n";
@@ -156,7 +374,8 @@ int main(int argc, char **argv)
         }
     }
     std::cout << "Number of reads: " << num_reads << std::endl;
-    std::cout << "Time elapsed (loading reads): " << ms_since(t0) << " msec" << std::endl;
+    const long load_reads_ms = ms_since(t0);
+    std::cout << "Time elapsed (loading reads): " << load_reads_ms << " msec" << std::endl;
     mark("fasta_loaded");
 
     devq.join();
@@ -167,6 +386,10 @@ int main(int argc, char **argv)
     }
     int want_gpus = ndev;
     if (const char *e = getenv("DARWIN_GPUS")) want_gpus = std::max(1, std::min(ndev, atoi(e)));
+    if (is_worker) {
+        if (wk_count > ndev) { fprintf(stderr, "darwin: %d worker processes but only %d CUDA device(s)\n", wk_count, ndev); return 2; }
+        want_gpus = wk_count;
+    }
     printf("Using GPU: %d device(s); CUDA driver initialised after %ld msec\n", want_gpus, devq_ms);
 
     // ---- shards: contiguous read ranges, one per GPU (darwin.cpp:619-629 rule) ----------------
@@ -178,8 +401,18 @@ int main(int argc, char **argv)
         s.tid = g; s.device = g;
         s.first_read = std::min(num_reads, per * g);
         s.last_read = std::min(num_reads, per * (g + 1));
-        s.dsoft_threads = std::max(1, num_threads / G);
+        s.dsoft_threads = is_worker ? num_threads : std::max(1, num_threads / G);
+        if (is_worker && g != wk_index) continue;          // a worker process owns exactly one shard
         if (s.first_read < s.last_read || g == 0) shards.push_back(s);
+    }
+    if (is_worker && shards.empty()) {
+        // more GPUs than reads: nothing to do for this worker, but the coordinator still waits for its two reports
+        report("READY {\"reads\": " + std::to_string(num_reads) + ", \"idle\": 1}");
+        char go = 0;
+        ssize_t r = read(3, &go, 1);
+        (void)r;
+        report("DONE {\"tiles\": 0, \"cells\": 0, \"candidates\": 0, \"error\": 0}");
+        return 0;
     }
 
     // ---- engines: one per shard/GPU, created and loaded while the seed table is being built -------
@@ -378,11 +611,8 @@ int main(int argc, char **argv)
             for (Batch &x : bt) { x.ga.resize(x.calls.size()); x.ga_dev.resize(x.gc.size()); }
             sh.text.assign(B, std::string());
             sh.dsoft_ms = ms_since(td);
-            {
-                std::lock_guard<std::mutex> lk(io_lock);
-                printf("num_candidates: %llu %llu\n", (unsigned long long)sh.cand_fwd, (unsigned long long)sh.cand_rev);
-                std::cout << "Time finding seeds: " << sh.dsoft_ms << " msec" << std::endl;
-            }
+            shard_print("num_candidates: " + std::to_string(sh.cand_fwd) + " " + std::to_string(sh.cand_rev));
+            shard_print("Time finding seeds: " + std::to_string(sh.dsoft_ms) + " msec");
             const auto tg = Clock::now();
             if (!slow_calls.empty()) {
                 // reads with exceptions: tile by tile through the host scheduler, before the chain batches are in flight
@@ -468,12 +698,9 @@ int main(int argc, char **argv)
             sh.stats.rounds = B;
             sh.gact_ms = ms_since(tg);
             sh.stats.wall_ms = (double)sh.gact_ms;
-            {
-                std::lock_guard<std::mutex> lk(io_lock);
-                std::cout << "Time GACT calling: " << sh.gact_ms << " msec (" << B << " batch(es) of chains; host blocked on chains "
-                          << (long)(sh.extend_wait_us / 1e3 + 0.5) << " msec; writer thread busy " << (long)(sh.write_us / 1e3 + 0.5)
-                          << " msec)" << std::endl;
-            }
+            shard_print("Time GACT calling: " + std::to_string(sh.gact_ms) + " msec (" + std::to_string(B) + " batch(es) of chains; host blocked on chains "
+                        + std::to_string((long)(sh.extend_wait_us / 1e3 + 0.5)) + " msec; writer thread busy "
+                        + std::to_string((long)(sh.write_us / 1e3 + 0.5)) + " msec)");
         } catch (const std::exception &e) {
             sh.error = e.what();
         }
@@ -670,6 +897,17 @@ int main(int argc, char **argv)
     {
         std::unique_lock<std::mutex> lk(gate_m);
         gate_cv.wait(lk, [&] { return parked == shards.size(); });
+        if (is_worker) {
+            // tell the coordinator that this GPU is ready, then wait for its "go": the bracket is the coordinator's
+            char buf[512];
+            snprintf(buf, sizeof(buf), "READY {\"reads\": %zu, \"reference_length\": %u, \"ref_pieces\": %zu, \"load_ref_ms\": %ld, "
+                     "\"load_reads_ms\": %ld, \"cuda_up_ms\": %ld, \"gpu_init_ms\": %ld, \"seed_table_phase_ms\": %ld, \"seed_table_ms\": %.1f, "
+                     "\"worker_setup_ms\": %.3f, \"ready_ms\": %.1f}", num_reads, reference_length, ref.seqs.size(), load_ref_ms, load_reads_ms,
+                     devq_ms, shards[0].init_ms, ms_since(t_gpu), shards[0].table_kernel_ms, shards[0].setup_us / 1e3, us_since(t_prog) / 1e3);
+            report(buf);
+            char gobyte = 0;
+            if (read(3, &gobyte, 1) != 1) _exit(4);          // the coordinator is gone
+        }
         mark("workers_parked_bracket_opens");
         t0 = Clock::now();
         go = true;
@@ -688,6 +926,20 @@ int main(int argc, char **argv)
         align_ms = (long)(align_us / 1e3 + 0.5);
     }
     mark("bracket_closes");
+    if (is_worker) {
+        const Shard &sh = shards[0];
+        if (!sh.error.empty()) fprintf(stderr, "shard %d: %s\n", sh.tid, sh.error.c_str());
+        char buf[512];
+        snprintf(buf, sizeof(buf), "DONE {\"tiles\": %llu, \"cells\": %llu, \"candidates\": %llu, \"align_phase_ms\": %.3f, "
+                 "\"gact_sched_ms\": %.1f, \"gact_kernel_ms\": %.1f, \"chain_batches\": %d, \"error\": %d}",
+                 (unsigned long long)sh.stats.tiles, (unsigned long long)sh.stats.cells, (unsigned long long)(sh.cand_fwd + sh.cand_rev),
+                 align_us / 1e3, sh.stats.wall_ms, sh.stats.device_ms, sh.batches, sh.error.empty() ? 0 : 1);
+        report(buf);
+        // the output file is closed and reported; the driver releases this process's context when it exits, which is
+        // faster than destroying engine, filter and seed table one by one (GPU_close comes after the reference's bracket too)
+        fflush(nullptr);
+        _exit(sh.error.empty() ? 0 : 3);
+    }
     const auto t_join = Clock::now();
     for (auto &w : workers) w.join();
     const long join_ms = ms_since(t_join);

@@ -133,15 +133,19 @@ def _gpu_count():
     return pygact.device_count()
 
 
+@pytest.mark.parametrize("multiproc", ["1", "0"])
 @pytest.mark.parametrize("gpus", [2, 4, 8])
-def test_multi_gpu_sharded_output_matches_cpu_build(tmp_path, gpus):
-    """Reads sharded over several GPUs (DARWIN_GPUS, one engine + host thread + darwin.<tid>.out per GPU): the concatenated,
-    sorted|uniq output is the reference CPU build's, whatever the shard count (config 4)."""
+def test_multi_gpu_sharded_output_matches_cpu_build(tmp_path, gpus, multiproc):
+    """Reads sharded over several GPUs (DARWIN_GPUS; one worker process per GPU by default, one host thread per GPU with
+    DARWIN_MULTIPROC=0; one engine and one darwin.<tid>.out per GPU either way): the concatenated, sorted|uniq output is
+    the reference CPU build's, whatever the shard count (config 4)."""
     if _gpu_count() < gpus:
         pytest.skip(f"needs {gpus} GPUs")
     for gold, cfgs, tag in ((ACGT, ACGT_CFGS, "t320"), (GOLD, CFGS, "t320")):
         got, out = run_darwin(str(tmp_path / f"{os.path.basename(gold)}_{gpus}"), os.path.join(gold, "ref.fasta"),
-                              os.path.join(gold, "reads.fasta"), 4, cfgs[tag], env={"DARWIN_GPUS": str(gpus)})
+                              os.path.join(gold, "reads.fasta"), 4, cfgs[tag],
+                              env={"DARWIN_GPUS": str(gpus), "DARWIN_MULTIPROC": multiproc, "DARWIN_SORTED_OUT": "out.darwin"})
+        assert open(os.path.join(str(tmp_path / f"{os.path.basename(gold)}_{gpus}"), "out.darwin")).read().splitlines() == got
         assert got == open(os.path.join(gold, f"expected_{tag}.txt")).read().splitlines()
         assert f"Using GPU: {gpus} device(s)" in out
         files = [fn for fn in os.listdir(str(tmp_path / f"{os.path.basename(gold)}_{gpus}")) if fn.startswith("darwin.") and fn.endswith(".out")]
