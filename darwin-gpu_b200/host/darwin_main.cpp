@@ -300,6 +300,27 @@ int main(int argc, char **argv)
         num_threads = std::max(1, num_threads / wk_count);
     }
     const bool is_worker = wk_index >= 0;
+    // The CUDA driver enumerates every visible GPU when it starts (5 s on an 8-GPU box): a worker process, and a run that
+    // uses one GPU, only need their own device -- narrow CUDA_VISIBLE_DEVICES before the first CUDA call.
+    int device_base = 0;                                   // device index of shard 0 inside this process
+    {
+        const int want = getenv("DARWIN_GPUS") ? atoi(getenv("DARWIN_GPUS")) : 0;
+        const int mine = is_worker ? wk_index : (want == 1 ? 0 : -1);
+        if (mine >= 0) {
+            std::string pick = std::to_string(mine);
+            if (const char *vis = getenv("CUDA_VISIBLE_DEVICES")) {
+                std::vector<std::string> ids;
+                std::string cur;
+                for (const char *c = vis;; c++) {
+                    if (*c == ',' || *c == 0) { ids.push_back(cur); cur.clear(); if (*c == 0) break; }
+                    else cur.push_back(*c);
+                }
+                pick = (size_t)mine < ids.size() ? ids[(size_t)mine] : std::string("none");
+            }
+            setenv("CUDA_VISIBLE_DEVICES", pick.c_str(), 1);
+            device_base = -mine;                           // shard `mine` is device 0 of this process
+        }
+    }
     auto report = [&](const std::string &line) {               // worker -> coordinator
         const std::string l = line + "\n";
         ssize_t r = write(4, l.data(), l.size());
@@ -387,8 +408,7 @@ int main(int argc, char **argv)
     int want_gpus = ndev;
     if (const char *e = getenv("DARWIN_GPUS")) want_gpus = std::max(1, std::min(ndev, atoi(e)));
     if (is_worker) {
-        if (wk_count > ndev) { fprintf(stderr, "darwin: %d worker processes but only %d CUDA device(s)\n", wk_count, ndev); return 2; }
-        want_gpus = wk_count;
+        want_gpus = wk_count;                              // this process sees its own device only
     }
     printf("Using GPU: %d device(s); CUDA driver initialised after %ld msec\n", want_gpus, devq_ms);
 
@@ -398,7 +418,7 @@ int main(int argc, char **argv)
     std::vector<Shard> shards;
     for (int g = 0; g < G; g++) {
         Shard s;
-        s.tid = g; s.device = g;
+        s.tid = g; s.device = g + device_base;
         s.first_read = std::min(num_reads, per * g);
         s.last_read = std::min(num_reads, per * (g + 1));
         s.dsoft_threads = is_worker ? num_threads : std::max(1, num_threads / G);
@@ -549,6 +569,12 @@ int main(int argc, char **argv)
             if (!fout.is_open()) { sh.error = "ERROR cannot open output file"; return; }
             const auto td = Clock::now();
             gact_engine *eng = sh.eng;
+            // DARWIN_TRACE=1: microsecond checkpoints of this shard's align phase (where the host time goes)
+            const bool trace = getenv("DARWIN_TRACE") != nullptr;
+            std::string trace_line;
+            auto tmark = [&](const char *what) {
+                if (trace) { char b[96]; snprintf(b, sizeof(b), " %s %.0f", what, us_since(td)); trace_line += b; }
+            };
 
             // ---- D-SOFT: queries = (reads, k), (reverse-complemented reads, k) for every read of the shard ----
             std::vector<int32_t> qsets(2 * nr);
@@ -566,6 +592,7 @@ int main(int argc, char **argv)
             }
             if (rc) { sh.error = std::string("gact_dsoft_run: ") + gact_last_error(eng); return; }
             sh.dsoft_wait_us = us_since(td);
+            tmark("dsoft_done");
 
             // ---- batches of consecutive reads ----
             size_t per_batch = nr;
@@ -609,6 +636,7 @@ int main(int argc, char **argv)
                 x.gc_pos.push_back(x.calls.size() - 1);
             }
             for (Batch &x : bt) { x.ga.resize(x.calls.size()); x.ga_dev.resize(x.gc.size()); }
+            tmark("calls_built");
             sh.text.assign(B, std::string());
             sh.dsoft_ms = ms_since(td);
             shard_print("num_candidates: " + std::to_string(sh.cand_fwd) + " " + std::to_string(sh.cand_rev));
@@ -688,10 +716,13 @@ int main(int argc, char **argv)
             for (size_t b = 0; b < B && !rc; b++) {
                 while (!rc && b - collected >= (size_t)GACT_MAX_INFLIGHT) rc = extend_collect(collected++);
                 if (!rc) rc = gact_engine_extend_submit(eng, (int)bt[b].gc.size(), bt[b].gc.data());
+                tmark("submitted");
             }
-            while (!rc && collected < B) rc = extend_collect(collected++);
+            while (!rc && collected < B) { rc = extend_collect(collected++); tmark("collected"); }
             if (rc) { finish_writer(true); sh.error = std::string("gact_engine_extend: ") + gact_last_error(eng); return; }
             finish_writer(false);
+            tmark("written");
+            if (trace) shard_print("TRACE shard " + std::to_string(sh.tid) + " (us since the shard started):" + trace_line);
             gact_stats es;
             gact_engine_stats(eng, &es);
             sh.stats.device_ms = es.kernel_ms;

@@ -54,6 +54,6 @@ for g in gpus:
                   f"wall_s {wall:.2f} same_output {uniq == base} lines {len(uniq)}")
             if rep == 1:
                 for ln in r.stdout.splitlines():
-                    if ln.startswith("Time ") or ln.startswith("GPU "):
+                    if ln.startswith("Time ") or ln.startswith("GPU ") or ln.startswith("TRACE"):
                         print("    " + ln)
                 print("    timeline", tl)
