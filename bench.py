@@ -317,16 +317,16 @@ def reads_leg(n_gpus, cpu_arm_reads=200):
             res["reference_cpu"] = {"unavailable": "oracle/_ref/darwin_ref not built"}
         # ---- weak scaling: n_gpus x 50 MB ----
         if n_gpus > 1:
+            # every GPU gets the same work as the single GPU of the strong-scaling run: the 50 MB read set replicated
+            # n_gpus times (names prefixed), so per-GPU work is exactly fixed as N grows
             all_names, all_reads = list(names), list(reads)
             for r in range(1, n_gpus):
-                nm, rd = synth.sample_reads(genome, 50_000_000, np.random.default_rng(4 + 100 * r), mean=10000, sd=3000,
-                                            lo=1000, hi=30000, prefix=f"W{r}x")
-                all_names += nm
-                all_reads += rd
+                all_names += [f"W{r}x{nm}" for nm in names]
+                all_reads += reads
             # replicas are concatenated: the contiguous shards of ceil(N / G) reads are then one replica each
             synth.write_fasta(os.path.join(wd, "reads_weak.fasta"), all_names, all_reads)
-            weak, sub_weak = ours("reads_weak.fasta", len(all_reads), f"weak scaling: {n_gpus} x 50 MB of the same read profile "
-                                                                     "vs the same 100 Mbp reference")
+            weak, sub_weak = ours("reads_weak.fasta", len(all_reads), f"weak scaling: the 50 MB read set replicated {n_gpus} x (one replica "
+                                                                     "per GPU) vs the same 100 Mbp reference")
             res["weak"] = weak
             if ref_lines is not None:
                 res["weak_sorted_uniq_identical_on_subset"] = bool(ref_lines == sub_weak)

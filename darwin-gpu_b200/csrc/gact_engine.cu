@@ -1195,10 +1195,26 @@ int gact_dsoft_wait(gact_dsoft *d, gact_dsoft_cand *out, int64_t out_cap, int64_
     if (total > b.limit || (int64_t)total > out_cap) return fail(e, GACT_ERR_NOMEM, "candidate buffer too small (see *n_out)");
     if (total) {
         static_assert(sizeof(DsoftCand) == sizeof(gact_dsoft_cand), "candidate layouts differ");
-        memcpy(out, b.h_out, (size_t)total * sizeof(gact_dsoft_cand));
-        std::sort(out, out + total, [](const gact_dsoft_cand &a, const gact_dsoft_cand &c) {
-            return a.query != c.query ? a.query < c.query : a.seq < c.seq;
-        });
+        // group by query, emission order inside a query: every candidate carries its query and its index inside that
+        // query, so its final position is known without a comparison sort
+        std::vector<uint32_t> start((size_t)b.n_queries + 1, 0);
+        bool ok = true;
+        for (unsigned long long i = 0; i < total && ok; i++) {
+            const int32_t q = b.h_out[i].query;
+            if (q < 0 || q >= b.n_queries) ok = false; else start[(size_t)q + 1]++;
+        }
+        for (int q = 0; q < b.n_queries; q++) start[(size_t)q + 1] += start[(size_t)q];
+        for (unsigned long long i = 0; i < total && ok; i++) {
+            const gact_dsoft_cand &c = b.h_out[i];
+            const uint32_t pos = start[(size_t)c.query] + (uint32_t)c.seq;
+            if (c.seq < 0 || pos >= start[(size_t)c.query + 1]) ok = false; else out[pos] = c;
+        }
+        if (!ok) {                                         // cannot happen with a well-formed candidate stream
+            memcpy(out, b.h_out, (size_t)total * sizeof(gact_dsoft_cand));
+            std::sort(out, out + total, [](const gact_dsoft_cand &a, const gact_dsoft_cand &c) {
+                return a.query != c.query ? a.query < c.query : a.seq < c.seq;
+            });
+        }
         e->stats.d2h_bytes += (double)total * sizeof(DsoftCand);
     }
     return GACT_OK;

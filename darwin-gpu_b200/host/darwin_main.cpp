@@ -79,6 +79,7 @@ struct Shard {
     double dsoft_wait_us = 0, extend_wait_us = 0, write_us = 0;   // pipelined path: host time blocked on the device / writing
     int batches = 0;
     std::vector<std::string> text;             // output of the shard, one string per batch (for DARWIN_SORTED_OUT)
+    std::vector<uint8_t> read_exc;             // per read of the shard: holds a byte other than ACGT (tile-by-tile path)
     uint64_t cand_fwd = 0, cand_rev = 0;
     std::string error;
     gact_engine *eng = nullptr;               // created before the align phase (like GPU_init, darwin.cpp:611)
@@ -460,8 +461,11 @@ int main(int argc, char **argv)
             upload(GACT_SET_READS, reads.seqs, S.first_read, S.last_read);
             upload(GACT_SET_READS_RC, rev_reads, S.first_read, S.last_read);
             bool slow_reads = false;                      // reads with bytes other than ACGT take the tile-by-tile path
-            for (size_t k = 0; k < S.last_read - S.first_read && !slow_reads; k++)
-                slow_reads = gact_engine_seq_has_exceptions(S.eng, GACT_SET_READS, (int64_t)k) == 1;
+            S.read_exc.assign(S.last_read - S.first_read, 0);
+            for (size_t k = 0; k < S.last_read - S.first_read; k++) {
+                S.read_exc[k] = gact_engine_seq_has_exceptions(S.eng, GACT_SET_READS, (int64_t)k) == 1;
+                slow_reads |= S.read_exc[k] != 0;
+            }
             if (use_chains && gact_engine_extend_supported(S.eng)) gact_engine_extend_reserve(S.eng, (int)(8 * (S.last_read - S.first_read) + 1024));
             if (slow_reads || !(use_chains && gact_engine_extend_supported(S.eng)))
                 gact_engine_reserve_tiles(S.eng);         // tile-by-tile host scheduler: its batch slots belong to initialisation
@@ -595,9 +599,12 @@ int main(int argc, char **argv)
             tmark("dsoft_done");
 
             // ---- batches of consecutive reads ----
+            // one batch unless the shard has very many candidates (de-novo self-alignments: 200 k for config 1): the chains of
+            // one batch pack best (longest first over the whole shard); several batches only pay where the writer's work and
+            // the result copies of batch k are worth hiding behind the chains of batch k+1
             size_t per_batch = nr;
             if (batch_reads_set) per_batch = batch_reads_env ? batch_reads_env : nr;
-            else if (nr > 1800) { const size_t nb = (nr + 1199) / 1200; per_batch = (nr + nb - 1) / nb; }
+            else if (n_cands > 49152) { const size_t nb = ((size_t)n_cands + 32767) / 32768; per_batch = (nr + nb - 1) / nb; }
             per_batch = std::max<size_t>(per_batch, 1);
             const size_t B = std::max<size_t>(1, (nr + per_batch - 1) / per_batch);
             sh.batches = (int)B;
@@ -611,6 +618,11 @@ int main(int argc, char **argv)
             std::vector<std::pair<size_t, size_t>> slow_at;           // (batch, index in calls)
             // candidates arrive grouped by query (= read, strand) in emission order, i.e. in the reference CPU build's
             // order per read: forward candidates, then reverse (darwin.cpp:209-288)
+            {
+                std::vector<size_t> per((size_t)B, 0);
+                for (int64_t i = 0; i < n_cands; i++) per[std::min(B - 1, (size_t)(cands[(size_t)i].query >> 1) / per_batch)]++;
+                for (size_t b = 0; b < B; b++) { bt[b].calls.reserve(per[b]); bt[b].gc.reserve(per[b]); bt[b].gc_pos.reserve(per[b]); }
+            }
             for (int64_t i = 0; i < n_cands; i++) {
                 const gact_dsoft_cand &c = cands[(size_t)i];
                 const bool comp = (c.query & 1) != 0;
@@ -623,7 +635,7 @@ int main(int argc, char **argv)
                 const size_t bi = std::min(B - 1, local / per_batch);
                 Batch &x = bt[bi];
                 x.calls.push_back(GactCall{chr, (int32_t)local, ref_pos, (int)c.offset, (uint8_t)(comp ? 1 : 0)});
-                if (gact_engine_seq_has_exceptions(eng, GACT_SET_READS, (int64_t)local) == 1) {
+                if (sh.read_exc[local]) {
                     slow_calls.push_back(x.calls.back());
                     slow_at.emplace_back(bi, x.calls.size() - 1);
                     continue;
@@ -676,17 +688,32 @@ int main(int argc, char **argv)
                     }
                     const auto tw = Clock::now();
                     const Batch &x = bt[b];
+                    // formatted in parallel chunks (same line order as the sequential loop), one write per batch
+                    const int parts = std::max(1, std::min(sh.dsoft_threads, (int)(x.calls.size() / 1024) + 1));
+                    std::vector<std::string> piece((size_t)parts);
+                    auto fmt = [&](int p) {
+                        const size_t a0 = x.calls.size() * (size_t)p / parts, a1 = x.calls.size() * (size_t)(p + 1) / parts;
+                        std::string &o = piece[(size_t)p];
+                        o.reserve((a1 - a0) * 112);
+                        for (size_t k = a0; k < a1; k++) {
+                            const GactCall &c = x.calls[k];
+                            const size_t read_id = sh.first_read + (size_t)c.query_id;
+                            const gact_alignment &a = x.ga[k];
+                            if (!(same_file && (size_t)c.ref_id == read_id) && a.score > 0)        // gact.cpp:213
+                                o += format_overlap(ref.names[c.ref_id], reads.names[read_id],
+                                                    GactAlignment{a.ab, a.ae, a.bb, a.be, a.score, a.first_tile_score, a.n_tiles, a.n_cells},
+                                                    c.complement != 0);
+                        }
+                    };
+                    std::vector<std::thread> helpers;
+                    for (int p = 1; p < parts; p++) helpers.emplace_back(fmt, p);
+                    fmt(0);
+                    for (auto &h : helpers) h.join();
                     std::string &out = sh.text[b];
-                    out.reserve(x.calls.size() * 112);
-                    for (size_t k = 0; k < x.calls.size(); k++) {
-                        const GactCall &c = x.calls[k];
-                        const size_t read_id = sh.first_read + (size_t)c.query_id;
-                        const gact_alignment &a = x.ga[k];
-                        if (!(same_file && (size_t)c.ref_id == read_id) && a.score > 0)        // gact.cpp:213
-                            out += format_overlap(ref.names[c.ref_id], reads.names[read_id],
-                                                  GactAlignment{a.ab, a.ae, a.bb, a.be, a.score, a.first_tile_score, a.n_tiles, a.n_cells},
-                                                  c.complement != 0);
-                    }
+                    size_t total = 0;
+                    for (auto &o : piece) total += o.size();
+                    out.reserve(total);
+                    for (auto &o : piece) out += o;
                     fout.write(out.data(), (std::streamsize)out.size());
                     sh.write_us += us_since(tw);
                 }
