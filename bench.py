@@ -591,11 +591,11 @@ def main():
             smsp = 4 * 148
             inst = ncu["smsp__inst_executed.sum"] / ncu["tiles"]                 # warp instructions per tile
             issue = {"source": os.path.relpath(NCU_SUMMARY, ROOT), "capture": ncu.get("capture"),
-                     "warp_inst_per_tile": inst, "alu_pipe_warp_inst_per_tile": ncu.get("sm__inst_executed_pipe_alu.sum", 0) / ncu["tiles"],
-                     "fma_pipe_warp_inst_per_tile": ncu.get("sm__inst_executed_pipe_fma.sum", 0) / ncu["tiles"],
+                     "warp_inst_per_tile": inst, "alu_pipe_warp_inst_per_tile": ncu.get("alu_pipe_warp_inst", 0) / ncu["tiles"],
+                     "fma_pipe_warp_inst_per_tile": ncu.get("fma_pipe_warp_inst", 0) / ncu["tiles"],
                      # one warp instruction per cycle per SM sub-partition is the issue peak; the ALU pipe takes one every two cycles
                      "issue_slot_frac": inst * tiles_per_s / (smsp * sm_clock_hz),
-                     "alu_pipe_frac": (ncu.get("sm__inst_executed_pipe_alu.sum", 0) / ncu["tiles"]) * tiles_per_s / (smsp * sm_clock_hz * 0.5),
+                     "alu_pipe_frac": (ncu.get("alu_pipe_warp_inst", 0) / ncu["tiles"]) * tiles_per_s / (smsp * sm_clock_hz * 0.5),
                      "alu_pipe_busy_ncu_pct": ncu.get("sm__inst_executed_pipe_alu.sum.pct_of_peak_sustained_active"),
                      "issue_active_ncu_pct": ncu.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                      "sm_clock_mhz_used": sm_clock_hz / 1e6}

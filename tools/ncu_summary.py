@@ -57,6 +57,11 @@ if len(sys.argv) > 4:
                 rec["unit_of"][h] = u
             except ValueError:
                 rec[h] = v
+    # pipe attribution of the executed SASS mix (warp instructions): ALU pipe = logic / min-max / permute / compare / add,
+    # FMA pipe = IMAD family
+    ALU = ("LOP3", "VIADDMNMX", "VIMNMX3", "VIMNMX", "PRMT", "IADD3", "SEL", "VIADD", "ISETP", "LEA", "SHF", "PLOP3", "HSET2", "IABS", "IADD", "LOP", "BREV", "FLO", "POPC")
+    rec["alu_pipe_warp_inst"] = sum(c for k, c in ops.items() if k.split(".")[0] in ALU)
+    rec["fma_pipe_warp_inst"] = sum(c for k, c in ops.items() if k.split(".")[0] == "IMAD")
     rec["sass_instructions_executed"] = tot
     rec["instruction_mix"] = {k: c for k, c in sorted(ops.items(), key=lambda kv: -kv[1])[:24]}
     json.dump(rec, open(sys.argv[3], "w"), indent=1)
