@@ -16,6 +16,7 @@
 #include "gact_kernels_i32.cuh"
 #include "gact_kernels_s16.cuh"
 #include "gact_kernels_s16h.cuh"
+#include "gact_kernels_it.cuh"
 #include "dsoft.cuh"
 #include "seed_build.cuh"
 #include <algorithm>
@@ -60,6 +61,9 @@ struct Slot {
     int *d_counters = nullptr;            // [0] first pass, [1] main pass, [2] / [3] the same for the raw-byte group
     int n_lut = 0, n_first_lut = 0;       // tiles / first tiles whose query window has no exception: they come first in
                                           // h_order / h_first and run on the score-table kernels, the rest on raw bytes
+    int n_it = 0;                         // leading part of the n_lut tiles that goes to the inter-task kernel (multiple of 64)
+    int *d_escaped = nullptr;             // tiles the inter-task kernel handed back (band left): redone by the wavefront kernel
+    int *h_it_info = nullptr;             // pinned: [0] batches claimed, [1] tiles handed back, of this slot's last launch
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr, ev_h2d = nullptr, ev_fork = nullptr;
     int n = 0, n_first = 0;
     bool busy = false;
@@ -92,12 +96,19 @@ struct gact_engine {
     uint8_t *d_gscratch = nullptr;
     S16HPlan s16h;            // packed s16x2 kernels: two tiles per warp (tile_size <= 320) or one (<= 1024); ok = usable for these params
     S16HPlan s16h_lat;        // chain kernel, one tile per warp: used when candidates < chain slots (latency bound)
+    // inter-task tile kernel (gact_kernels_it.cuh): one lane per pair of full, non-first tiles
+    bool it_ok = false;       // usable for these parameters
+    ITGeom it_geom{};
+    int it_ctas = 0, it_min_tiles = 0;
+    uint8_t *d_it_scratch = nullptr;      // GACT_MAX_INFLIGHT regions: strip edges, row score tables, code words per resident warp
+    size_t it_region_bytes = 0, it_edge_b = 0, it_lut_b = 0, it_win_b = 0;
     SeqSetHost sets[GACT_MAX_SETS];
     Slot slots[GACT_MAX_INFLIGHT];
     int head = 0, tail = 0, inflight = 0;   // async ring
     bool staged = false;
     bool slots_ready = false;
     double last_kernel_ms = -1.0;
+    int last_n_it = 0, last_n_escaped = 0;   // inter-task kernel: tiles it took / handed back in the last finished batch
     struct gact_chain_state *chains = nullptr;       // gact_engine_extend_* state (created on first use)
     gact_stats stats{};
     std::string err;
@@ -172,6 +183,8 @@ void free_slot(Slot &s)
     if (s.d_order) cudaFree(s.d_order);
     if (s.h_order) cudaFreeHost(s.h_order);
     if (s.d_counters) cudaFree(s.d_counters);
+    if (s.d_escaped) cudaFree(s.d_escaped);
+    if (s.h_it_info) cudaFreeHost(s.h_it_info);
     if (s.h_descs) cudaFreeHost(s.h_descs);
     if (s.h_results) cudaFreeHost(s.h_results);
     if (s.h_states) cudaFreeHost(s.h_states);
@@ -273,6 +286,21 @@ int plan_launch(gact_engine *e)
     if (s16h_make_plan(e->params, e->num_sms, wps, &e->s16h) != 0 ||
         s16h_make_plan(e->params, e->num_sms, wps, &e->s16h_lat, true) != 0)
         return fail(e, GACT_ERR_CUDA, "s16h kernel attribute setup failed");
+    // inter-task kernel: full, non-first tiles, one lane per pair of tiles (experiment knobs: GACT_IT=0 switches it off,
+    // GACT_IT_BAND=<half-width of the tagged band>, GACT_IT_MIN=<fewest eligible tiles of a batch worth a launch>)
+    e->it_ok = false;
+    const char *itv = getenv("GACT_IT");
+    if (e->s16h.ok && e->s16h.lut_ok && T % IT_CS == 0 && T / IT_CS <= IT_MAX_STRIPS && T >= 64 && !(itv && atoi(itv) == 0)) {
+        int W = 32;
+        if (const char *b = getenv("GACT_IT_BAND")) W = std::max(4, atoi(b));
+        e->it_geom = it_geometry(T, et, W);
+        e->it_ctas = 4 * e->num_sms;                                   // 4 CTAs x 4 warps per SM
+        e->it_min_tiles = 64 * 4 * e->num_sms;                         // one warp per SM sub-partition at least
+        if (const char *m = getenv("GACT_IT_MIN")) e->it_min_tiles = std::max(64, atoi(m));
+        e->it_edge_b = it_edge_bytes(T); e->it_lut_b = it_lut_bytes(T); e->it_win_b = it_win_bytes(e->it_geom);
+        e->it_region_bytes = (size_t)e->it_ctas * 4 * (e->it_edge_b + e->it_lut_b + e->it_win_b);
+        e->it_ok = true;                                               // scratch is allocated with the batch slots
+    }
     return GACT_OK;
 }
 
@@ -285,7 +313,7 @@ bool use_s16(const gact_engine *e)
 int launch_batch(gact_engine *e, Slot &s, cudaStream_t st, int scratch_region)
 {
     CU(e, cudaStreamWaitEvent(st, s.ev_h2d, 0));        // descriptors of this batch are on the device
-    CU(e, cudaMemsetAsync(s.d_counters, 0, 4 * sizeof(int), st));
+    CU(e, cudaMemsetAsync(s.d_counters, 0, 8 * sizeof(int), st));
     CU(e, cudaEventRecord(s.ev_k0, st));
     const int TS = e->C * 32;
     if (use_s16(e)) {
@@ -300,9 +328,32 @@ int launch_batch(gact_engine *e, Slot &s, cudaStream_t st, int scratch_region)
             s16h_launch_first(e->s16h, e->kp, s.d_descs, s.d_first + s.n_first_lut, nf_byte, s.d_eff, s.d_counters + 2, st, false);
             e->stats.kernel_launches++;
         }
-        if (s.n_lut > 0) {
-            s16h_launch(e->s16h, e->kp, s.d_descs, s.d_order, s.n_lut, s.d_eff, s.d_results, s.d_states, e->pitch_words,
-                        s.d_counters + 1, st, scratch_region, true);
+        if (s.n_it > 0) {
+            KParams kp = e->kp;
+            kp.s16_bias = e->s16h.bias;
+            kp.one = 1;
+            const int n_batches = s.n_it / 64;
+            int grid = (n_batches + 3) / 4;
+            if (grid > e->it_ctas) grid = e->it_ctas;
+            uint8_t *base = e->d_it_scratch + (size_t)scratch_region * e->it_region_bytes;
+            const size_t warps = (size_t)e->it_ctas * 4;
+            uint2 *edge = reinterpret_cast<uint2 *>(base);
+            uint2 *lut = reinterpret_cast<uint2 *>(base + warps * e->it_edge_b);
+            uint32_t *win = reinterpret_cast<uint32_t *>(base + warps * (e->it_edge_b + e->it_lut_b));
+            gact_tile_it_kernel<<<grid, 128, 0, st>>>(kp, e->it_geom, s.d_descs, s.d_order, n_batches, s.d_results, s.d_states,
+                                                      e->pitch_words, s.d_counters + 4, s.d_escaped, edge, lut, win, e->it_win_b / 4);
+            e->stats.kernel_launches++;
+        }
+        if (s.n_lut - s.n_it > 0) {
+            s16h_launch(e->s16h, e->kp, s.d_descs, s.d_order + s.n_it, s.n_lut - s.n_it, s.d_eff, s.d_results, s.d_states,
+                        e->pitch_words, s.d_counters + 1, st, scratch_region, true);
+            e->stats.kernel_launches++;
+        }
+        if (s.n_it > 0) {
+            // tiles whose traceback left the band: redone with the full window; their number stays on the device
+            const int bound = std::min(s.n_it, e->s16h.ctas * e->s16h.warps_per_cta * e->s16h.tpw());
+            s16h_launch(e->s16h, e->kp, s.d_descs, s.d_escaped, bound, s.d_eff, s.d_results, s.d_states, e->pitch_words,
+                        s.d_counters + 6, st, scratch_region, true, s.d_counters + 5);
             e->stats.kernel_launches++;
         }
         if (n_byte > 0) {
@@ -338,34 +389,50 @@ int check_descs(gact_engine *e, int n, const gact_tile_desc *descs, Slot &s)
     const int T = e->params.tile_size;
     unsigned long long cells = 0;
     const bool table_ok = use_s16(e) && e->s16h.lut_ok;
-    // group 0: score-table kernels, group 1: raw-byte kernels
+    // group 0: inter-task kernel (full, non-first tiles of the score-table group), 1: score-table wavefront kernels,
+    // 2: raw-byte wavefront kernels
+    const bool it_on = table_ok && e->it_ok && e->d_it_scratch && s.d_escaped;
     std::vector<uint8_t> grp((size_t)n, 0);
-    int cnt[2] = {0, 0}, nf[2] = {0, 0};
+    int cnt[3] = {0, 0, 0}, nf[3] = {0, 0, 0};
     for (int t = 0; t < n; t++) {
         const gact_tile_desc &d = descs[t];
         if (d.ref_set >= GACT_MAX_SETS || d.query_set >= GACT_MAX_SETS || d.ref_len < 0 || d.query_len < 0 ||
             d.ref_len > T || d.query_len > T || d.ref_off < 0 || d.query_off < 0 ||
             d.ref_off + d.ref_len > e->sets[d.ref_set].len || d.query_off + d.query_len > e->sets[d.query_set].len)
             return fail(e, GACT_ERR_ARG, "tile descriptor " + std::to_string(t) + " out of range");
-        const int g = (table_ok && !e->sets[d.query_set].range_has_exc(d.query_off, d.query_len)) ? 0 : 1;
+        int g = (table_ok && !e->sets[d.query_set].range_has_exc(d.query_off, d.query_len)) ? 1 : 2;
+        if (g == 1 && it_on && !d.first && d.ref_len == T && d.query_len == T) g = 0;
         grp[(size_t)t] = (uint8_t)g;
         cnt[g]++;
         if (d.first) nf[g]++;
         cells += (unsigned long long)d.ref_len * (unsigned long long)d.query_len;
     }
-    s.n_lut = cnt[0];
-    s.n_first_lut = nf[0];
-    s.n_first = nf[0] + nf[1];
+    // the inter-task kernel takes whole warps of 64 tiles and only batches that fill the GPU; the rest joins group 1
+    int n_it = (cnt[0] / 64) * 64;
+    if (n_it < e->it_min_tiles) n_it = 0;
+    {
+        int spill = cnt[0] - n_it;
+        for (int t = n - 1; t >= 0 && spill > 0; t--)
+            if (grp[(size_t)t] == 0) { grp[(size_t)t] = 1; spill--; }
+        cnt[1] += cnt[0] - n_it;
+        cnt[0] = n_it;
+    }
+    s.n_it = n_it;
+    s.n_lut = cnt[0] + cnt[1];
+    s.n_first_lut = nf[1];
+    s.n_first = nf[1] + nf[2];
     s.cells = cells;
-    int fpos[2] = {0, nf[0]};
+    int fpos[3] = {0, 0, nf[1]};
     for (int t = 0; t < n; t++) if (descs[t].first) s.h_first[fpos[grp[(size_t)t]]++] = t;
-    // counting sort by reference length inside each group, longest first: the two tiles a warp aligns side by side
-    // then have the same number of wavefront steps, and the long tiles start first
-    std::vector<int> start(2 * ((size_t)T + 2), 0);
-    auto bucket = [&](int t) { return (size_t)grp[(size_t)t] * ((size_t)T + 1) + (size_t)(T - descs[t].ref_len); };
-    for (int t = 0; t < n; t++) start[bucket(t) + 1]++;
+    // h_order: [inter-task tiles, in input order][score-table tiles][raw-byte tiles]; the wavefront groups are counting-
+    // sorted by reference length, longest first: the two tiles a warp aligns side by side then have the same number of
+    // wavefront steps, and the long tiles start first
+    std::vector<int> start(2 * ((size_t)T + 2) + 1, 0);
+    auto bucket = [&](int t) { return (size_t)(grp[(size_t)t] - 1) * ((size_t)T + 1) + (size_t)(T - descs[t].ref_len); };
+    int pos_it = 0;
+    for (int t = 0; t < n; t++) { if (grp[(size_t)t] == 0) s.h_order[pos_it++] = t; else start[bucket(t) + 1]++; }
     for (size_t k = 1; k < start.size(); k++) start[k] += start[k - 1];
-    for (int t = 0; t < n; t++) s.h_order[start[bucket(t)]++] = t;
+    for (int t = 0; t < n; t++) if (grp[(size_t)t] != 0) s.h_order[n_it + start[bucket(t)]++] = t;
     return GACT_OK;
 }
 
@@ -395,6 +462,7 @@ int download(gact_engine *e, Slot &s, bool want_states)
     // next batch's kernels do not wait for the copy
     CU(e, cudaStreamWaitEvent(e->s_d2h, s.ev_k1, 0));
     CU(e, cudaMemcpyAsync(s.h_results, s.d_results, (size_t)s.n * sizeof(gact_tile_result), cudaMemcpyDeviceToHost, e->s_d2h));
+    if (s.n_it > 0) CU(e, cudaMemcpyAsync(s.h_it_info, s.d_counters + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->s_d2h));
     e->stats.d2h_bytes += (double)s.n * sizeof(gact_tile_result);
     if (want_states) {
         CU(e, cudaMemcpyAsync(s.h_states, s.d_states, (size_t)s.n * e->pitch_words * 4, cudaMemcpyDeviceToHost, e->s_d2h));
@@ -411,6 +479,8 @@ int finish(gact_engine *e, Slot &s, gact_tile_result *results, uint32_t *packed_
         CU(e, cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
         e->last_kernel_ms = ms;
         e->stats.kernel_ms += ms;
+        e->last_n_it = s.n_it;
+        e->last_n_escaped = s.n_it > 0 ? s.h_it_info[1] : 0;
         if (results) memcpy(results, s.h_results, (size_t)s.n * sizeof(gact_tile_result));
         if (packed_states && states_copied) memcpy(packed_states, s.h_states, (size_t)s.n * e->pitch_words * 4);
     }
@@ -426,6 +496,15 @@ int finish(gact_engine *e, Slot &s, gact_tile_result *results, uint32_t *packed_
 int ensure_slots(gact_engine *e)
 {
     if (e->slots_ready) return GACT_OK;
+    if (e->it_ok && e->max_tiles >= e->it_min_tiles && !e->d_it_scratch) {
+        if (cudaMalloc(&e->d_it_scratch, (size_t)GACT_MAX_INFLIGHT * e->it_region_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            e->d_it_scratch = nullptr;
+            e->it_ok = false;                 // not enough memory for the scratch: the wavefront kernels take every tile
+        }
+    } else if (e->it_ok && e->max_tiles < e->it_min_tiles) {
+        e->it_ok = false;                     // batches of this engine are too small to fill the GPU with one lane per tile pair
+    }
     for (int k = 0; k < GACT_MAX_INFLIGHT; k++) {
         Slot &s = e->slots[k];
         const size_t n = (size_t)e->max_tiles;
@@ -436,7 +515,10 @@ int ensure_slots(gact_engine *e)
         CU(e, cudaMalloc(&s.d_first, n * sizeof(int)));
         CU(e, cudaMalloc(&s.d_order, n * sizeof(int)));
         CU(e, cudaMallocHost(&s.h_order, n * sizeof(int)));
-        CU(e, cudaMalloc(&s.d_counters, 4 * sizeof(int)));
+        CU(e, cudaMalloc(&s.d_counters, 8 * sizeof(int)));
+        if (e->it_ok) CU(e, cudaMalloc(&s.d_escaped, n * sizeof(int)));
+        CU(e, cudaMallocHost(&s.h_it_info, 2 * sizeof(int)));
+        s.h_it_info[0] = s.h_it_info[1] = 0;
         CU(e, cudaMallocHost(&s.h_descs, n * sizeof(gact_tile_desc)));
         CU(e, cudaMallocHost(&s.h_results, n * sizeof(gact_tile_result)));
         CU(e, cudaMallocHost(&s.h_states, n * e->pitch_words * 4));
@@ -554,6 +636,7 @@ void gact_engine_destroy(gact_engine *e)
     for (int i = 0; i < GACT_MAX_SETS; i++) free_set(e->sets[i]);
     for (int k = 0; k < GACT_MAX_INFLIGHT; k++) free_slot(e->slots[k]);
     if (e->d_gscratch) cudaFree(e->d_gscratch);
+    if (e->d_it_scratch) cudaFree(e->d_it_scratch);
     s16h_free_plan(&e->s16h);
     s16h_free_plan(&e->s16h_lat);
     destroy_chain_state(e);
@@ -835,10 +918,20 @@ int gact_engine_fetch_staged(gact_engine *e, gact_tile_result *results, uint32_t
     CU(e, cudaStreamSynchronize(e->s_d2h));
     CU(e, cudaStreamSynchronize(e->stream));
     if (s.n > 0) {
+        e->last_n_it = s.n_it;
+        e->last_n_escaped = s.n_it > 0 ? s.h_it_info[1] : 0;
         if (results) memcpy(results, s.h_results, (size_t)s.n * sizeof(gact_tile_result));
         if (packed_states) memcpy(packed_states, s.h_states, (size_t)s.n * e->pitch_words * 4);
     }
     e->staged = false;
+    return GACT_OK;
+}
+
+int gact_engine_tile_path_info(const gact_engine *e, int *n_inter_task, int *n_handed_back)
+{
+    if (!e) return GACT_ERR_ARG;
+    if (n_inter_task) *n_inter_task = e->last_n_it;
+    if (n_handed_back) *n_handed_back = e->last_n_escaped;
     return GACT_OK;
 }
 

@@ -607,10 +607,12 @@ __global__ void __launch_bounds__(128, (CS <= 10 ? 4 : 2))
 gact_tile_s16h_kernel(const __grid_constant__ KParams P, const gact_tile_desc *__restrict__ descs,
                       const int *__restrict__ order, int n_tiles, const EffLen *__restrict__ eff,
                       gact_tile_result *__restrict__ results, uint32_t *__restrict__ states,
-                      int pitch_words, int *counter, size_t seq_bytes, uint8_t *gscratch, size_t dir_bytes)
+                      int pitch_words, int *counter, size_t seq_bytes, uint8_t *gscratch, size_t dir_bytes,
+                      const int *__restrict__ n_ptr)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int TPW = 32 / LANES;
+    if (n_ptr) n_tiles = *n_ptr;              // list length produced on the device (tiles the inter-task kernel handed back)
     SegCtx<CS, LANES> cx;
     cx.init(P, smem, threadIdx.x >> 5, seq_bytes, gscratch, dir_bytes, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), LUT);
     const int lane = cx.lane, seg = cx.seg, sl = cx.sl;
@@ -951,7 +953,7 @@ struct S16HPlan {
 };
 
 typedef void (*s16h_fn)(const KParams, const gact_tile_desc *, const int *, int, const EffLen *, gact_tile_result *,
-                        uint32_t *, int, int *, size_t, uint8_t *, size_t);
+                        uint32_t *, int, int *, size_t, uint8_t *, size_t, const int *);
 typedef void (*s16h_first_fn)(const KParams, const gact_tile_desc *, const int *, int, EffLen *, int *, size_t);
 typedef void (*s16h_chain_fn)(const KParams, const ChainCall *, int, ChainResult *, int, ChainAux *, int *, size_t, uint8_t *,
                               size_t, int, int, int);
@@ -1109,15 +1111,16 @@ inline void s16h_launch_first(const S16HPlan &pl, KParams kp, const gact_tile_de
 
 inline void s16h_launch(const S16HPlan &pl, KParams kp, const gact_tile_desc *descs, const int *order, int n,
                         const EffLen *eff, gact_tile_result *results, uint32_t *states, int pitch_words, int *counter,
-                        cudaStream_t st, int scratch_region, bool lut)
+                        cudaStream_t st, int scratch_region, bool lut, const int *n_ptr = nullptr)
 {
     kp.win_rows = pl.win_rows;
     kp.win_lanes = pl.win_lanes;
     kp.s16_bias = pl.bias;
     kp.one = 1;
+    // n_ptr: the list length is on the device (n is then only an upper bound used to size the grid)
     s16h_pick(pl.CS, pl.lanes, lut)<<<s16h_grid(pl, n), pl.warps_per_cta * 32, pl.smem, st>>>(
         kp, descs, order, n, eff, results, states, pitch_words, counter, pl.seq_bytes,
-        pl.d_scratch + (size_t)scratch_region * pl.scratch_bytes, pl.dir_bytes);
+        pl.d_scratch + (size_t)scratch_region * pl.scratch_bytes, pl.dir_bytes, n_ptr);
 }
 
 }  // namespace gact

@@ -55,7 +55,7 @@ EXPORTS = [
     "gact_engine_last_kernel_ms", "gact_engine_stats", "gact_engine_reset_stats",
     "gact_engine_set_kernel", "gact_engine_get_kernel", "gact_int_peak",
     "gact_engine_extend", "gact_engine_extend_supported", "gact_engine_extend_reserve", "gact_dsoft_reserve",
-    "gact_engine_extend_submit", "gact_engine_extend_wait", "gact_engine_reserve_tiles", "gact_engine_set_chain_mode", "gact_engine_chain_info",
+    "gact_engine_extend_submit", "gact_engine_extend_wait", "gact_engine_reserve_tiles", "gact_engine_tile_path_info", "gact_engine_set_chain_mode", "gact_engine_chain_info",
     "gact_dsoft_create", "gact_dsoft_destroy", "gact_dsoft_run", "gact_dsoft_last_kernel_ms", "gact_dsoft_submit", "gact_dsoft_wait",
     "gact_seed_table_build", "gact_seed_table_destroy", "gact_seed_table_info", "gact_seed_table_download",
     "gact_dsoft_create_from_table",
@@ -243,6 +243,12 @@ class GactEngine:
 
     def set_bits(self, set_id):
         return self.L.gact_engine_set_bits(self.h, set_id)
+
+    def tile_path_info(self):
+        a, b = C.c_int(0), C.c_int(0)
+        self.L.gact_engine_tile_path_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        self._ck(self.L.gact_engine_tile_path_info(self.h, C.byref(a), C.byref(b)), "gact_engine_tile_path_info")
+        return {"inter_task": a.value, "handed_back": b.value}
 
     def seq_has_exceptions(self, set_id, i):
         return self.L.gact_engine_seq_has_exceptions(self.h, set_id, i)

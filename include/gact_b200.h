@@ -207,6 +207,10 @@ int gact_engine_sync(gact_engine *e);
  * (CUDA events on the engine stream); <0 if none. */
 double gact_engine_last_kernel_ms(gact_engine *e);
 
+/* Diagnostics of the last finished tile batch: how many tiles the inter-task kernel took (full, non-first tiles of large
+ * batches; one lane per pair of tiles, pointers only for a band around the diagonal) and how many of them it handed back
+ * to the wavefront kernel because their traceback left that band.  Results never depend on the routing. */
+int gact_engine_tile_path_info(const gact_engine *e, int *n_inter_task, int *n_handed_back);
 /* Optional: allocate the batch slots of the tile path now (they are otherwise allocated by the first tile batch). */
 int gact_engine_reserve_tiles(gact_engine *e);
 int gact_engine_stats(const gact_engine *e, gact_stats *out);

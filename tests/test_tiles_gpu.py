@@ -189,6 +189,41 @@ def test_empty_and_tiny_tiles(pygact, variant):
         assert len(res0) == 0
 
 
+@pytest.mark.parametrize("band", ["32", "5"])
+@pytest.mark.parametrize("tile,overlap,scores", [(320, 120, (1, -1, -1, -1)), (256, 96, (2, -3, -5, -2)), (320, 0, (1, -1, -2, -1)),
+                                                 (512, 192, (1, -1, -1, -1)), (64, 10, (1, -3, 0, 0)), (1024, 384, (1, -1, -1, -1))])
+def test_inter_task_kernel_matches_oracle(pygact, oracle, monkeypatch, band, tile, overlap, scores):
+    """Full, non-first tiles of a batch on the inter-task kernel (one lane per pair of tiles, direction codes only for a band
+    around the diagonal); with a 5-wide band most tracebacks leave it and the tiles are handed back to the wavefront kernel.
+    Every tile of the mixed batch (full / edge / first, reference with N runs) must equal the oracle either way."""
+    G, O = pygact, oracle
+    import synth
+    monkeypatch.setenv("GACT_IT_MIN", "64")
+    monkeypatch.setenv("GACT_IT_BAND", band)
+    n = 700 if tile >= 512 else 2600
+    mb = synth.tile_microbatch(n, tile_size=tile, seed=tile + int(band), full_frac=0.9, first_frac=0.1)
+    ref = mb["ref"].copy()
+    rng = np.random.default_rng(2)
+    for _ in range(12):                                   # exceptions in the reference stay on the score-table path
+        p = int(rng.integers(0, len(ref) - 100))
+        ref[p:p + int(rng.integers(1, 60))] = ord("N")
+    mb["ref"] = ref
+    with G.GactEngine(*scores, tile_size=tile, tile_overlap=overlap, max_tiles=n) as eng:
+        eng.upload(G.SET_REF, [ref.tobytes()])
+        eng.upload(G.SET_READS, [mb["query"].tobytes()])
+        res, st = eng.align_tiles(engine_descs(G, mb))
+        info = eng.tile_path_info()
+    eligible = int(((mb["ref_len"] == tile) & (mb["query_len"] == tile) & (mb["first"] == 0)).sum())
+    assert info["inter_task"] == (eligible // 64) * 64 and info["inter_task"] > 0.5 * n
+    if band == "5":
+        assert info["handed_back"] > 0                             # a 15 % error channel wanders more than 5 off the diagonal
+    elif scores == (1, -1, -1, -1):
+        assert info["handed_back"] < 0.05 * info["inter_task"]
+    ores, ost = O.align_batch(ref, mb["query"], oracle_descs(O, mb), scores=scores, et=tile - overlap, max_len=tile, n_threads=8)
+    bad = compare_batch(res, st, ores, ost)
+    assert len(bad) == 0, f"{len(bad)} of {n} tiles differ, first {bad[:5]}: gpu {res[bad[:3]]} cpu {ores[bad[:3]]}"
+
+
 def test_async_submit_wait_matches_sync(pygact):
     G = pygact
     import synth
