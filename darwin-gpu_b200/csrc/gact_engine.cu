@@ -101,7 +101,7 @@ struct gact_engine {
     ITGeom it_geom{};
     int it_ctas = 0, it_min_tiles = 0;
     uint8_t *d_it_scratch = nullptr;      // GACT_MAX_INFLIGHT regions: strip edges, row score tables, code words per resident warp
-    size_t it_region_bytes = 0, it_edge_b = 0, it_lut_b = 0, it_win_b = 0;
+    size_t it_region_bytes = 0, it_edge_b = 0, it_win_b = 0, it_smem = 0;
     SeqSetHost sets[GACT_MAX_SETS];
     Slot slots[GACT_MAX_INFLIGHT];
     int head = 0, tail = 0, inflight = 0;   // async ring
@@ -291,15 +291,18 @@ int plan_launch(gact_engine *e)
     e->it_ok = false;
     const char *itv = getenv("GACT_IT");
     if (e->s16h.ok && e->s16h.lut_ok && T % IT_CS == 0 && T / IT_CS <= IT_MAX_STRIPS && T >= 64 && !(itv && atoi(itv) == 0)) {
-        int W = 32;
+        int W = std::max(32, (et + 7) / 8);         // a 15 % error channel drifts ~0.045 et off the diagonal, +- 0.37 sqrt(et)
         if (const char *b = getenv("GACT_IT_BAND")) W = std::max(4, atoi(b));
         e->it_geom = it_geometry(T, et, W);
         e->it_ctas = 4 * e->num_sms;                                   // 4 CTAs x 4 warps per SM
         e->it_min_tiles = 64 * 4 * e->num_sms;                         // one warp per SM sub-partition at least
         if (const char *m = getenv("GACT_IT_MIN")) e->it_min_tiles = std::max(64, atoi(m));
-        e->it_edge_b = it_edge_bytes(T); e->it_lut_b = it_lut_bytes(T); e->it_win_b = it_win_bytes(e->it_geom);
-        e->it_region_bytes = (size_t)e->it_ctas * 4 * (e->it_edge_b + e->it_lut_b + e->it_win_b);
-        e->it_ok = true;                                               // scratch is allocated with the batch slots
+        e->it_edge_b = it_edge_bytes(T); e->it_win_b = it_win_bytes(e->it_geom);
+        e->it_region_bytes = (size_t)e->it_ctas * 4 * (e->it_edge_b + e->it_win_b);
+        e->it_smem = 4 * it_smem_per_warp(T);
+        e->it_ok = cudaFuncSetAttribute((const void *)gact_tile_it_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)e->it_smem) == cudaSuccess;      // scratch is allocated with the batch slots
+        if (!e->it_ok) cudaGetLastError();
     }
     return GACT_OK;
 }
@@ -338,10 +341,9 @@ int launch_batch(gact_engine *e, Slot &s, cudaStream_t st, int scratch_region)
             uint8_t *base = e->d_it_scratch + (size_t)scratch_region * e->it_region_bytes;
             const size_t warps = (size_t)e->it_ctas * 4;
             uint2 *edge = reinterpret_cast<uint2 *>(base);
-            uint2 *lut = reinterpret_cast<uint2 *>(base + warps * e->it_edge_b);
-            uint32_t *win = reinterpret_cast<uint32_t *>(base + warps * (e->it_edge_b + e->it_lut_b));
-            gact_tile_it_kernel<<<grid, 128, 0, st>>>(kp, e->it_geom, s.d_descs, s.d_order, n_batches, s.d_results, s.d_states,
-                                                      e->pitch_words, s.d_counters + 4, s.d_escaped, edge, lut, win, e->it_win_b / 4);
+            uint32_t *win = reinterpret_cast<uint32_t *>(base + warps * e->it_edge_b);
+            gact_tile_it_kernel<<<grid, 128, e->it_smem, st>>>(kp, e->it_geom, s.d_descs, s.d_order, n_batches, s.d_results, s.d_states,
+                                                              e->pitch_words, s.d_counters + 4, s.d_escaped, edge, win, e->it_win_b / 4);
             e->stats.kernel_launches++;
         }
         if (s.n_lut - s.n_it > 0) {
@@ -401,7 +403,7 @@ int check_descs(gact_engine *e, int n, const gact_tile_desc *descs, Slot &s)
             d.ref_off + d.ref_len > e->sets[d.ref_set].len || d.query_off + d.query_len > e->sets[d.query_set].len)
             return fail(e, GACT_ERR_ARG, "tile descriptor " + std::to_string(t) + " out of range");
         int g = (table_ok && !e->sets[d.query_set].range_has_exc(d.query_off, d.query_len)) ? 1 : 2;
-        if (g == 1 && it_on && !d.first && d.ref_len == T && d.query_len == T) g = 0;
+        if (g == 1 && it_on && !d.first && d.ref_len == T && d.query_len == T && e->sets[d.ref_set].h_exc.empty()) g = 0;
         grp[(size_t)t] = (uint8_t)g;
         cnt[g]++;
         if (d.first) nf[g]++;

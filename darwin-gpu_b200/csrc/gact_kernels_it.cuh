@@ -9,7 +9,10 @@
 // around the diagonal inside the traceback window (14 % of the row-steps at W = 32), there is no wavefront skew, no
 // shuffle and no per-step edge bookkeeping.  Price: a lane sweeps its tiles strip by strip (CS columns in registers),
 // and the strip's right edge (H and D of every row) goes through a per-warp scratch array in global memory to the next
-// strip -- 16 bytes per row and lane, coalesced, about 1 byte per cell pair.
+// strip -- 16 bytes per row and lane, coalesced, about 1 byte per cell pair.  The reference rows' score tables cost no
+// memory traffic: the tile's reference is re-packed into DP order in shared memory (2 bits per row, 16 rows per word, the
+// same alignment for every lane) and the 4-byte table of a row is one PRMT in "backward 4 extract" mode on the
+// constant (match, mismatch, mismatch, mismatch), selected by the two low bits of the shifted word.
 //
 // Eligible tiles (the engine routes them, check_descs): ref_len == query_len == tile_size, not a first tile, query
 // window free of exceptions (the score-table path), tile_size a multiple of CS.  A traceback that leaves the band is
@@ -23,6 +26,7 @@
 namespace gact {
 
 constexpr int IT_CS = 16;             // columns of a strip (per tile); 4 code words per row
+constexpr int IT_PF = 8;              // rows ahead an edge entry is prefetched into L1
 constexpr int IT_MAX_STRIPS = 64;     // tile_size <= 1024
 
 struct ITGeom {
@@ -55,14 +59,26 @@ inline ITGeom it_geometry(int T, int et, int W)
     return g;
 }
 // per resident warp, in bytes
-inline size_t it_edge_bytes(int T) { return (size_t)(T + 1) * 32 * sizeof(uint2); }
-inline size_t it_lut_bytes(int T) { return (size_t)(T + 2) * 32 * sizeof(uint2); }
+inline size_t it_edge_bytes(int T) { return (size_t)(T + 1 + IT_PF) * 32 * sizeof(uint2); }
+// shared memory per warp: both tiles' reference rows, 2 bits per row
+inline size_t it_smem_per_warp(int T) { return (size_t)2 * ((T + 15) / 16) * 32 * sizeof(uint32_t); }
 inline size_t it_win_bytes(const ITGeom &g) { return (size_t)g.win_off[IT_MAX_STRIPS] * (IT_CS / 4) * 32 * sizeof(uint32_t); }
+
+__device__ __forceinline__ void it_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // 2-bit code of base `pos` of a packed set
 __device__ __forceinline__ uint32_t it_code(const uint32_t *__restrict__ packed, long long pos)
 {
     return (__ldg(packed + (pos >> 4)) >> (2 * (int)(pos & 15))) & 3u;
+}
+
+// 4-byte score table of a reference row: `base` = (match, mismatch, mismatch, mismatch) * 16 rotated so that byte [code]
+// is the match score; only the two low bits of `w` (the row's 2-bit code) are looked at
+__device__ __forceinline__ uint32_t it_row_table(uint32_t base, uint32_t w)
+{
+    uint32_t r;
+    asm("prmt.b32.b4e %0, %1, %1, %2;" : "=r"(r) : "r"(base), "r"(w));
+    return r;
 }
 
 // One tile's view of the code words its lane wrote: code of cell (i, j), or -1 if the cell lies outside the band.
@@ -137,23 +153,27 @@ gact_tile_it_kernel(const __grid_constant__ KParams P, const __grid_constant__ I
                     const gact_tile_desc *__restrict__ descs, const int *__restrict__ order, int n_batches,
                     gact_tile_result *__restrict__ results, uint32_t *__restrict__ states, int pitch_words,
                     int *counters, int *__restrict__ escaped,
-                    uint2 *edge_scratch, uint2 *lut_scratch, uint32_t *win_scratch, size_t win_words_per_warp)
+                    uint2 *edge_scratch, uint32_t *win_scratch, size_t win_words_per_warp)
 {
+    extern __shared__ __align__(16) uint32_t it_smem[];
     constexpr int CS = IT_CS, NW = CS / 4;
     int lane;
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
     const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int T = G.T, S = G.S;
-    uint2 *edge = edge_scratch + (size_t)gwarp * (T + 1) * 32 + lane;           // edge[i * 32]: (H pair, D pair) of row i
-    uint2 *lut = lut_scratch + (size_t)gwarp * (T + 2) * 32 + lane;             // lut[i * 32]: score tables of row i (tile A, tile B)
+    uint2 *edge = edge_scratch + (size_t)gwarp * (T + 1 + IT_PF) * 32 + lane;   // edge[i * 32]: (H pair, D pair) of row i
+    const int RW = (T + 15) / 16;                                               // words of reference rows per tile
+    uint32_t *rowsA = it_smem + (size_t)(threadIdx.x >> 5) * 2 * RW * 32 + lane;  // rowsA[k * 32]: rows 16k+1 .. 16k+16 of tile A
+    uint32_t *rowsB = rowsA + (size_t)RW * 32;
     uint32_t *win = win_scratch + (size_t)gwarp * win_words_per_warp + lane;
     // constants of the biased x16 domain (as SegCtx)
     const int B = P.s16_bias;
     const uint32_t Bp = pk16(B), ge16 = pk16(P.gap_extend * 16);
     const int KO = (P.gap_open * 16) * 65537, KI = (P.gap_open * 16 - 5) * 65537, KD = (P.gap_open * 16 - 10) * 65537;
     const int ONE = P.one;
-    const uint32_t lut_mis = (uint32_t)((P.mismatch * 16) & 0xff) * 0x01010101u;
-    const uint32_t lut_delta = (uint32_t)(((P.match ^ P.mismatch) * 16) & 0xff);
+    // score table of a reference row with code c: byte [c] = match * 16, the others mismatch * 16 = this constant
+    // rotated by c bytes (prmt.b4e with the code in the two low bits of the selector)
+    const uint32_t lut_base = ((uint32_t)((P.mismatch * 16) & 0xff) * 0x01010100u) | (uint32_t)((P.match * 16) & 0xff);
     // left border of the tile: H[i][0] = 0; D[i][0] is chosen so that D[i][1] = gap_open with the open flag set, which is
     // what the reference's -inf border gives (align.cpp:87-97)
     const uint32_t borderG = Bp, borderD = pk16(B + P.gap_open * 16), borderD_tag = pk16(B + P.gap_open * 16 + 5);
@@ -170,15 +190,20 @@ gact_tile_it_kernel(const __grid_constant__ KParams P, const __grid_constant__ I
         const gact_tile_desc dA = descs[tA], dB = descs[tB];
         const SeqSetDev &rsA = P.sets[dA.ref_set], &qsA = P.sets[dA.query_set], &rsB = P.sets[dB.ref_set], &qsB = P.sets[dB.query_set];
 
-        // ---- score tables of every reference row (both tiles) ----
-        for (int i = 1; i <= T; i++) {
-            const long long pA = dA.ref_off + (dA.reverse ? (T - i) : (i - 1)), pB = dB.ref_off + (dB.reverse ? (T - i) : (i - 1));
-            uint32_t wa = lut_mis ^ (lut_delta << (8 * it_code(rsA.packed, pA)));
-            uint32_t wb = lut_mis ^ (lut_delta << (8 * it_code(rsB.packed, pB)));
-            if (rsA.exc && ((__ldg(rsA.exc + (pA >> 5)) >> (int)(pA & 31)) & 1u)) wa = lut_mis;
-            if (rsB.exc && ((__ldg(rsB.exc + (pB >> 5)) >> (int)(pB & 31)) & 1u)) wb = lut_mis;
-            lut[(size_t)i * 32] = make_uint2(wa, wb);
+        // ---- both tiles' reference rows in DP order, 2 bits per row, into shared memory ----
+        for (int k = 0; k < RW; k++) {
+            uint32_t wa = 0, wb = 0;
+            for (int r = 0; r < 16; r++) {
+                const int i = 16 * k + 1 + r;
+                if (i <= T) {
+                    wa |= it_code(rsA.packed, dA.ref_off + (dA.reverse ? (T - i) : (i - 1))) << (2 * r);
+                    wb |= it_code(rsB.packed, dB.ref_off + (dB.reverse ? (T - i) : (i - 1))) << (2 * r);
+                }
+            }
+            rowsA[(size_t)k * 32] = wa;
+            rowsB[(size_t)k * 32] = wb;
         }
+        __syncwarp();
 
         uint32_t cornerG = Bp;
         for (int s = 0; s < S; s++) {
@@ -204,12 +229,15 @@ gact_tile_it_kernel(const __grid_constant__ KParams P, const __grid_constant__ I
             const bool has_band = bhi >= blo;
             const int u1_end = has_band ? blo - 1 : T;                  // rows 1 .. u1_end untagged
 
+            uint32_t wA = 0, wB = 0;                                    // reference rows of the current group of 16, shifted as they are used
             int i = 1;
             // ---------------- untagged rows above the band ----------------
             for (; i <= u1_end; i++) {
                 uint32_t inG = borderG, inD = borderD;
-                if (!first_strip) { const uint2 e = edge[(size_t)i * 32]; inG = e.x; inD = e.y & 0xfff0fff0u; }
-                const uint2 rw = lut[(size_t)i * 32];
+                if (!first_strip) { const uint2 e = edge[(size_t)i * 32]; inG = e.x; inD = e.y & 0xfff0fff0u; it_prefetch(edge + (size_t)(i + IT_PF) * 32); }
+                if (((i - 1) & 15) == 0) { wA = rowsA[(size_t)((i - 1) >> 4) * 32]; wB = rowsB[(size_t)((i - 1) >> 4) * 32]; }
+                const uint2 rw = make_uint2(it_row_table(lut_base, wA), it_row_table(lut_base, wB));
+                wA >>= 2; wB >>= 2;
                 uint32_t hd = diag, dv = inD, mo = 0;
 #pragma unroll
                 for (int c = 0; c < CS; c++) {
@@ -237,8 +265,10 @@ gact_tile_it_kernel(const __grid_constant__ KParams P, const __grid_constant__ I
                 uint32_t *wp = win + (size_t)G.win_off[s] * NW * 32;
                 for (; i <= bhi; i++) {
                     uint32_t inG = borderG, inD = borderD_tag;
-                    if (!first_strip) { const uint2 e = edge[(size_t)i * 32]; inG = e.x; inD = e.y; }
-                    const uint2 rw = lut[(size_t)i * 32];
+                    if (!first_strip) { const uint2 e = edge[(size_t)i * 32]; inG = e.x; inD = e.y; it_prefetch(edge + (size_t)(i + IT_PF) * 32); }
+                    if (((i - 1) & 15) == 0) { wA = rowsA[(size_t)((i - 1) >> 4) * 32]; wB = rowsB[(size_t)((i - 1) >> 4) * 32]; }
+                    const uint2 rw = make_uint2(it_row_table(lut_base, wA), it_row_table(lut_base, wB));
+                    wA >>= 2; wB >>= 2;
                     uint32_t hd = diag, dv = inD;                             // tagged, with the flag of this strip's first column
                     uint32_t acc[NW];
 #pragma unroll
@@ -270,8 +300,10 @@ gact_tile_it_kernel(const __grid_constant__ KParams P, const __grid_constant__ I
                 }
                 for (; i <= T; i++) {
                     uint32_t inG = borderG, inD = borderD;
-                    if (!first_strip) { const uint2 e = edge[(size_t)i * 32]; inG = e.x; inD = e.y & 0xfff0fff0u; }
-                    const uint2 rw = lut[(size_t)i * 32];
+                    if (!first_strip) { const uint2 e = edge[(size_t)i * 32]; inG = e.x; inD = e.y & 0xfff0fff0u; it_prefetch(edge + (size_t)(i + IT_PF) * 32); }
+                    if (((i - 1) & 15) == 0) { wA = rowsA[(size_t)((i - 1) >> 4) * 32]; wB = rowsB[(size_t)((i - 1) >> 4) * 32]; }
+                    const uint2 rw = make_uint2(it_row_table(lut_base, wA), it_row_table(lut_base, wB));
+                    wA >>= 2; wB >>= 2;
                     uint32_t hd = diag, dv = inD, mo = 0;
 #pragma unroll
                     for (int c = 0; c < CS; c++) {

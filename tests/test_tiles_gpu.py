@@ -195,19 +195,15 @@ def test_empty_and_tiny_tiles(pygact, variant):
 def test_inter_task_kernel_matches_oracle(pygact, oracle, monkeypatch, band, tile, overlap, scores):
     """Full, non-first tiles of a batch on the inter-task kernel (one lane per pair of tiles, direction codes only for a band
     around the diagonal); with a 5-wide band most tracebacks leave it and the tiles are handed back to the wavefront kernel.
-    Every tile of the mixed batch (full / edge / first, reference with N runs) must equal the oracle either way."""
+    Every tile of the mixed batch (full / edge / first) must equal the oracle either way.  (A reference set with bytes other
+    than ACGT keeps all its tiles on the wavefront kernels: test_exceptions_routed_per_tile.)"""
     G, O = pygact, oracle
     import synth
     monkeypatch.setenv("GACT_IT_MIN", "64")
     monkeypatch.setenv("GACT_IT_BAND", band)
     n = 700 if tile >= 512 else 2600
     mb = synth.tile_microbatch(n, tile_size=tile, seed=tile + int(band), full_frac=0.9, first_frac=0.1)
-    ref = mb["ref"].copy()
-    rng = np.random.default_rng(2)
-    for _ in range(12):                                   # exceptions in the reference stay on the score-table path
-        p = int(rng.integers(0, len(ref) - 100))
-        ref[p:p + int(rng.integers(1, 60))] = ord("N")
-    mb["ref"] = ref
+    ref = mb["ref"]
     with G.GactEngine(*scores, tile_size=tile, tile_overlap=overlap, max_tiles=n) as eng:
         eng.upload(G.SET_REF, [ref.tobytes()])
         eng.upload(G.SET_READS, [mb["query"].tobytes()])
