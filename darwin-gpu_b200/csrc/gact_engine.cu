@@ -64,6 +64,8 @@ struct Slot {
     int n_it = 0;                         // leading part of the n_lut tiles that goes to the inter-task kernel (multiple of 64)
     int *d_escaped = nullptr;             // tiles the inter-task kernel handed back (band left): redone by the wavefront kernel
     int *h_it_info = nullptr;             // pinned: [0] batches claimed, [1] tiles handed back, of this slot's last launch
+    cudaStream_t st_it = nullptr;         // the inter-task kernel's own stream: the wavefront kernels of the same batch fill its tail
+    cudaEvent_t ev_it0 = nullptr, ev_it1 = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr, ev_h2d = nullptr, ev_fork = nullptr;
     int n = 0, n_first = 0;
     bool busy = false;
@@ -185,6 +187,9 @@ void free_slot(Slot &s)
     if (s.d_counters) cudaFree(s.d_counters);
     if (s.d_escaped) cudaFree(s.d_escaped);
     if (s.h_it_info) cudaFreeHost(s.h_it_info);
+    if (s.st_it) { cudaStreamSynchronize(s.st_it); cudaStreamDestroy(s.st_it); }
+    if (s.ev_it0) cudaEventDestroy(s.ev_it0);
+    if (s.ev_it1) cudaEventDestroy(s.ev_it1);
     if (s.h_descs) cudaFreeHost(s.h_descs);
     if (s.h_results) cudaFreeHost(s.h_results);
     if (s.h_states) cudaFreeHost(s.h_states);
@@ -294,7 +299,9 @@ int plan_launch(gact_engine *e)
         int W = std::max(32, (et + 7) / 8);         // a 15 % error channel drifts ~0.045 et off the diagonal, +- 0.37 sqrt(et)
         if (const char *b = getenv("GACT_IT_BAND")) W = std::max(4, atoi(b));
         e->it_geom = it_geometry(T, et, W);
-        e->it_ctas = 4 * e->num_sms;                                   // 4 CTAs x 4 warps per SM
+        int it_per_sm = 4;                                             // 4 CTAs x 4 warps per SM (experiment knob GACT_IT_CTAS)
+        if (const char *c = getenv("GACT_IT_CTAS")) it_per_sm = std::max(1, std::min(4, atoi(c)));
+        e->it_ctas = it_per_sm * e->num_sms;
         e->it_min_tiles = 64 * 4 * e->num_sms;                         // one warp per SM sub-partition at least
         if (const char *m = getenv("GACT_IT_MIN")) e->it_min_tiles = std::max(64, atoi(m));
         e->it_edge_b = it_edge_bytes(T); e->it_win_b = it_win_bytes(e->it_geom);
@@ -323,15 +330,9 @@ int launch_batch(gact_engine *e, Slot &s, cudaStream_t st, int scratch_region)
         // two groups (check_descs): tiles whose query window is free of exceptions score with the one-PRMT table from the
         // packed words; the others compare raw bytes (HSET2 path).  Same kernels otherwise, results land at the tile's index.
         const int n_byte = s.n - s.n_lut, nf_byte = s.n_first - s.n_first_lut;
-        if (s.n_first_lut > 0) {
-            s16h_launch_first(e->s16h, e->kp, s.d_descs, s.d_first, s.n_first_lut, s.d_eff, s.d_counters + 0, st, true);
-            e->stats.kernel_launches++;
-        }
-        if (nf_byte > 0) {
-            s16h_launch_first(e->s16h, e->kp, s.d_descs, s.d_first + s.n_first_lut, nf_byte, s.d_eff, s.d_counters + 2, st, false);
-            e->stats.kernel_launches++;
-        }
         if (s.n_it > 0) {
+            // full, non-first tiles: inter-task kernel on its own stream, launched first; its CTAs hold all registers of
+            // the SMs, so the wavefront kernels below start as its last wave drains and fill that tail
             KParams kp = e->kp;
             kp.s16_bias = e->s16h.bias;
             kp.one = 1;
@@ -342,8 +343,20 @@ int launch_batch(gact_engine *e, Slot &s, cudaStream_t st, int scratch_region)
             const size_t warps = (size_t)e->it_ctas * 4;
             uint2 *edge = reinterpret_cast<uint2 *>(base);
             uint32_t *win = reinterpret_cast<uint32_t *>(base + warps * e->it_edge_b);
-            gact_tile_it_kernel<<<grid, 128, e->it_smem, st>>>(kp, e->it_geom, s.d_descs, s.d_order, n_batches, s.d_results, s.d_states,
-                                                              e->pitch_words, s.d_counters + 4, s.d_escaped, edge, win, e->it_win_b / 4);
+            CU(e, cudaEventRecord(s.ev_it0, st));
+            CU(e, cudaStreamWaitEvent(s.st_it, s.ev_it0, 0));
+            gact_tile_it_kernel<<<grid, 128, e->it_smem, s.st_it>>>(kp, e->it_geom, s.d_descs, s.d_order, n_batches, s.d_results,
+                                                                    s.d_states, e->pitch_words, s.d_counters + 4, s.d_escaped, edge, win,
+                                                                    e->it_win_b / 4);
+            CU(e, cudaEventRecord(s.ev_it1, s.st_it));
+            e->stats.kernel_launches++;
+        }
+        if (s.n_first_lut > 0) {
+            s16h_launch_first(e->s16h, e->kp, s.d_descs, s.d_first, s.n_first_lut, s.d_eff, s.d_counters + 0, st, true);
+            e->stats.kernel_launches++;
+        }
+        if (nf_byte > 0) {
+            s16h_launch_first(e->s16h, e->kp, s.d_descs, s.d_first + s.n_first_lut, nf_byte, s.d_eff, s.d_counters + 2, st, false);
             e->stats.kernel_launches++;
         }
         if (s.n_lut - s.n_it > 0) {
@@ -351,16 +364,17 @@ int launch_batch(gact_engine *e, Slot &s, cudaStream_t st, int scratch_region)
                         e->pitch_words, s.d_counters + 1, st, scratch_region, true);
             e->stats.kernel_launches++;
         }
-        if (s.n_it > 0) {
-            // tiles whose traceback left the band: redone with the full window; their number stays on the device
-            const int bound = std::min(s.n_it, e->s16h.ctas * e->s16h.warps_per_cta * e->s16h.tpw());
-            s16h_launch(e->s16h, e->kp, s.d_descs, s.d_escaped, bound, s.d_eff, s.d_results, s.d_states, e->pitch_words,
-                        s.d_counters + 6, st, scratch_region, true, s.d_counters + 5);
-            e->stats.kernel_launches++;
-        }
         if (n_byte > 0) {
             s16h_launch(e->s16h, e->kp, s.d_descs, s.d_order + s.n_lut, n_byte, s.d_eff, s.d_results, s.d_states, e->pitch_words,
                         s.d_counters + 3, st, scratch_region, false);
+            e->stats.kernel_launches++;
+        }
+        if (s.n_it > 0) {
+            // tiles whose traceback left the band: redone with the full window; their number stays on the device
+            CU(e, cudaStreamWaitEvent(st, s.ev_it1, 0));
+            const int bound = std::min(s.n_it, e->s16h.ctas * e->s16h.warps_per_cta * e->s16h.tpw());
+            s16h_launch(e->s16h, e->kp, s.d_descs, s.d_escaped, bound, s.d_eff, s.d_results, s.d_states, e->pitch_words,
+                        s.d_counters + 6, st, scratch_region, true, s.d_counters + 5);
             e->stats.kernel_launches++;
         }
     } else {
@@ -520,6 +534,11 @@ int ensure_slots(gact_engine *e)
         CU(e, cudaMalloc(&s.d_counters, 8 * sizeof(int)));
         if (e->it_ok) CU(e, cudaMalloc(&s.d_escaped, n * sizeof(int)));
         CU(e, cudaMallocHost(&s.h_it_info, 2 * sizeof(int)));
+        if (e->it_ok) {
+            CU(e, cudaStreamCreateWithFlags(&s.st_it, cudaStreamNonBlocking));
+            CU(e, cudaEventCreateWithFlags(&s.ev_it0, cudaEventDisableTiming));
+            CU(e, cudaEventCreateWithFlags(&s.ev_it1, cudaEventDisableTiming));
+        }
         s.h_it_info[0] = s.h_it_info[1] = 0;
         CU(e, cudaMallocHost(&s.h_descs, n * sizeof(gact_tile_desc)));
         CU(e, cudaMallocHost(&s.h_results, n * sizeof(gact_tile_result)));

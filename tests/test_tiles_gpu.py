@@ -189,7 +189,7 @@ def test_empty_and_tiny_tiles(pygact, variant):
         assert len(res0) == 0
 
 
-@pytest.mark.parametrize("band", ["32", "5"])
+@pytest.mark.parametrize("band", ["default", "5"])
 @pytest.mark.parametrize("tile,overlap,scores", [(320, 120, (1, -1, -1, -1)), (256, 96, (2, -3, -5, -2)), (320, 0, (1, -1, -2, -1)),
                                                  (512, 192, (1, -1, -1, -1)), (64, 10, (1, -3, 0, 0)), (1024, 384, (1, -1, -1, -1))])
 def test_inter_task_kernel_matches_oracle(pygact, oracle, monkeypatch, band, tile, overlap, scores):
@@ -200,9 +200,10 @@ def test_inter_task_kernel_matches_oracle(pygact, oracle, monkeypatch, band, til
     G, O = pygact, oracle
     import synth
     monkeypatch.setenv("GACT_IT_MIN", "64")
-    monkeypatch.setenv("GACT_IT_BAND", band)
+    if band != "default":
+        monkeypatch.setenv("GACT_IT_BAND", band)          # default: max(32, early_terminate / 8)
     n = 700 if tile >= 512 else 2600
-    mb = synth.tile_microbatch(n, tile_size=tile, seed=tile + int(band), full_frac=0.9, first_frac=0.1)
+    mb = synth.tile_microbatch(n, tile_size=tile, seed=tile + len(band), full_frac=0.9, first_frac=0.1)
     ref = mb["ref"]
     with G.GactEngine(*scores, tile_size=tile, tile_overlap=overlap, max_tiles=n) as eng:
         eng.upload(G.SET_REF, [ref.tobytes()])
