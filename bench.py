@@ -45,7 +45,10 @@ OPS_PER_CELL_SURVEY = 17.0   # scalar int32 instructions p
 # adds run as IMAD on the FMA pipe), i.e. 2.5 ALU-pipe lane-operations per cell; direction codes, traceback, staging and
 # wavefront skew come on top, so achieved / peak computed from it cannot exceed 1.
 ALU_OPS_PER_CELL_FLOOR = 2.5
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r2_tile_kernel_ncu.json")     # this round's ncu capture of the tile kernel
+# this round's ncu captures of the two kernels of a tile step: the inter-task kernel (full, non-first tiles) and the
+# wavefront kernel (everything else)
+NCU_SUMMARIES = [("inter_task", os.path.join(ROOT, "profiles", "r2_inter_task_kernel_ncu.json")),
+                 ("wavefront", os.path.join(ROOT, "profiles", "r2_wavefront_kernel_ncu.json"))]
 TILE, OVERLAP = 320, 120
 SCORES = (1, -1, -1, -1)
 
@@ -57,7 +60,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tiles", type=int, default=1 << 20, help="tiles per GPU per step")
-    ap.add_argument("--chunk", type=int, default=1 << 16, help="tiles per submit() in the e2e leg")
+    ap.add_argument("--chunk", type=int, default=1 << 18, help="tiles per submit() in the e2e leg")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 int32, 2 s16x2")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -511,6 +514,7 @@ def main():
     dev_ms = ev[0].elapsed_time(ev[-1])
     per_step_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(args.steps)]
     res_dev, st_dev = eng.fetch_staged()
+    path_info = eng.tile_path_info()
 
     # ---- leg 2: end to end through the C ABI with host buffers (e2e) ----------------------
     chunk = min(args.chunk, n)
@@ -577,41 +581,53 @@ def main():
         packed = eng.get_kernel() == 2
         floor_ops = ALU_OPS_PER_CELL_FLOOR if packed else 2 * ALU_OPS_PER_CELL_FLOOR
         achieved = gcups_rank0 * floor_ops
-        # executed-instruction figures of the same kernel from this round's ncu capture (tools/ncu_summary.py -> profiles/);
-        # nothing from a profiler run is used as a bench value, the counters only turn the measured tile rate into pipe utilisation
-        ncu = None
-        try:
-            ncu = json.load(open(NCU_SUMMARY))
-        except Exception:
-            pass
-        issue = None
+        # executed-instruction figures of the step's kernels from this round's ncu captures (tools/ncu_summary.py -> profiles/);
+        # nothing from a profiler run is used as a bench value, the counters only turn the measured step time into pipe utilisation
+        issue, traffic = None, None
         sm_clock_hz = (clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
-        if ncu and packed and TILE == 320 and ncu.get("tiles"):
-            tiles_per_s = n / (kernel_ms * 1e-3)
-            smsp = 4 * 148
-            inst = ncu["smsp__inst_executed.sum"] / ncu["tiles"]                 # warp instructions per tile
-            issue = {"source": os.path.relpath(NCU_SUMMARY, ROOT), "capture": ncu.get("capture"),
-                     "warp_inst_per_tile": inst, "alu_pipe_warp_inst_per_tile": ncu.get("alu_pipe_warp_inst", 0) / ncu["tiles"],
-                     "fma_pipe_warp_inst_per_tile": ncu.get("fma_pipe_warp_inst", 0) / ncu["tiles"],
-                     # one warp instruction per cycle per SM sub-partition is the issue peak; the ALU pipe takes one every two cycles
-                     "issue_slot_frac": inst * tiles_per_s / (smsp * sm_clock_hz),
-                     "alu_pipe_frac": (ncu.get("alu_pipe_warp_inst", 0) / ncu["tiles"]) * tiles_per_s / (smsp * sm_clock_hz * 0.5),
-                     "alu_pipe_busy_ncu_pct": ncu.get("sm__inst_executed_pipe_alu.sum.pct_of_peak_sustained_active"),
-                     "issue_active_ncu_pct": ncu.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-                     "sm_clock_mhz_used": sm_clock_hz / 1e6}
-        traffic = None
-        if ncu and packed and TILE == 320 and ncu.get("tiles") and ncu.get("dram__bytes_read.sum") is not None:
-            traffic = (ncu["dram__bytes_read.sum"] + ncu["dram__bytes_write.sum"]) / ncu["tiles"] * n
-        roof = {"bound": "int_issue", "kernel": "gact_tile_s16h_kernel<10,16,true> (packed s16x2 DPX)" if packed else "gact_tile_i32 kernel",
+        if packed and TILE == 320:
+            caps = {}
+            for name, path in NCU_SUMMARIES:
+                try:
+                    caps[name] = json.load(open(path))
+                except Exception:
+                    pass
+            n_it = path_info["inter_task"]
+            cells_it = n_it * TILE * TILE
+            share = {"inter_task": cells_it, "wavefront": cells - cells_it}
+            if all(k in caps and caps[k].get("cells") for k, v in share.items() if v > 0):
+                smsp = 4 * 148
+                inst = sum(caps[k]["smsp__inst_executed.sum"] / caps[k]["cells"] * v for k, v in share.items() if v > 0)
+                alu = sum(caps[k].get("alu_pipe_warp_inst", 0) / caps[k]["cells"] * v for k, v in share.items() if v > 0)
+                fma = sum(caps[k].get("fma_pipe_warp_inst", 0) / caps[k]["cells"] * v for k, v in share.items() if v > 0)
+                traffic = sum((caps[k]["dram__bytes_read.sum"] + caps[k]["dram__bytes_write.sum"]) / caps[k]["cells"] * v
+                              for k, v in share.items() if v > 0)
+                issue = {"kernels": {k: {"source": os.path.relpath(dict(NCU_SUMMARIES)[k], ROOT), "capture": caps[k].get("capture"),
+                                         "cells_in_this_step": v, "warp_inst_per_cell": caps[k]["smsp__inst_executed.sum"] / caps[k]["cells"],
+                                         "alu_pipe_busy_ncu_pct": caps[k].get("sm__inst_executed_pipe_alu.sum.pct_of_peak_sustained_active"),
+                                         "issue_active_ncu_pct": caps[k].get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                                         "dram_bytes_per_cell": (caps[k]["dram__bytes_read.sum"] + caps[k]["dram__bytes_write.sum"]) / caps[k]["cells"]}
+                                     for k, v in share.items() if v > 0},
+                         "warp_inst_per_step": inst, "alu_pipe_warp_inst_per_step": alu, "fma_pipe_warp_inst_per_step": fma,
+                         # one warp instruction per cycle per SM sub-partition is the issue peak; the ALU pipe takes one every two cycles
+                         "issue_slot_frac": inst / (kernel_ms * 1e-3 * smsp * sm_clock_hz),
+                         "alu_pipe_frac": alu / (kernel_ms * 1e-3 * smsp * sm_clock_hz * 0.5),
+                         "sm_clock_mhz_used": sm_clock_hz / 1e6,
+                         "note": "the two kernels overlap on two streams; fractions are over the whole step"}
+        roof = {"bound": "int_issue",
+                "kernel": ("tile step = gact_tile_it_kernel (%d of %d tiles: full, non-first) overlapped with gact_first_s16h / "
+                           "gact_tile_s16h_kernel<10,16,true> (the rest), packed s16x2 DPX" % (path_info["inter_task"], n)) if packed
+                else "gact_tile_i32 kernel",
                 "achieved": achieved, "peak": peak_alu,
                 "unit": "G ALU-pipe lane-ops/s: achieved = cells/s x %.1f (algorithmic floor of the %s recurrence, 5 ALU-pipe "
                         "instructions per cell pair: PRMT score select, 3 VIADDMNMX, 1 VIMNMX3); peak = measured ALU-pipe issue rate "
                         "(gact_int_peak, VIADDMNMX, this run)" % (floor_ops, "packed s16x2" if packed else "int32"),
                 "frac": achieved / peak_alu,
                 "traffic": traffic,
-                "traffic_note": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of this kernel from this round's "
-                                "ncu --set full capture, scaled by tile count): the per-warp direction window (22 KB per tile, written once, "
-                                "read by the traceback) that does not stay in L2; algorithmic traffic is 0.3 KB per tile",
+                "traffic_note": "DRAM bytes per step (dram__bytes_read.sum + dram__bytes_write.sum of the step's kernels from this round's "
+                                "ncu --set full captures, scaled by the cells each kernel got): the inter-task kernel's strip edges "
+                                "(16 B per row, lane and strip) and the wavefront kernel's direction windows; algorithmic traffic is "
+                                "0.3 KB per tile",
                 "alu_ops_per_cell_floor": floor_ops, "lane_width": "s16x2" if packed else "s32",
                 "gcups_at_floor_roofline": peak_alu / floor_ops,
                 "executed": issue,
@@ -633,7 +649,9 @@ def main():
                 "e2e": {"value": e2e_gcups, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms_max / args.steps, "api": "gact_engine_submit/wait, %d batches of up to %d tiles (quarter/half-size batches at both ends), "
                                "%d in flight" % (len(bounds), chunk, G.MAX_INFLIGHT)},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+                "tile_routing": {"inter_task_kernel_tiles": path_info["inter_task"], "handed_back_to_wavefront_kernel": path_info["handed_back"],
+                                 "wavefront_kernel_tiles": n - path_info["inter_task"]}}
         if world == 1 and not args.no_cpu_baseline:
             small = {k: (v[:1 << 16] if k not in ("ref", "query") else v) for k, v in mb.items()}
             keep = ("value", "unit", "cores", "kind", "sample")

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <thread>
 #include <new>
 
 #include "gact_common.cuh"
@@ -112,6 +113,8 @@ struct gact_engine {
     double last_kernel_ms = -1.0;
     int last_n_it = 0, last_n_escaped = 0;   // inter-task kernel: tiles it took / handed back in the last finished batch
     struct gact_chain_state *chains = nullptr;       // gact_engine_extend_* state (created on first use)
+    std::vector<int> scratch_rest;                   // check_descs work arrays (kept to avoid reallocation per batch)
+    std::vector<uint8_t> scratch_grp;
     gact_stats stats{};
     std::string err;
 };
@@ -406,10 +409,14 @@ int check_descs(gact_engine *e, int n, const gact_tile_desc *descs, Slot &s)
     unsigned long long cells = 0;
     const bool table_ok = use_s16(e) && e->s16h.lut_ok;
     // group 0: inter-task kernel (full, non-first tiles of the score-table group), 1: score-table wavefront kernels,
-    // 2: raw-byte wavefront kernels
+    // 2: raw-byte wavefront kernels.  One pass: inter-task tiles go straight into h_order (their order does not matter),
+    // the others are collected and counting-sorted afterwards (they are the minority of a large batch).
     const bool it_on = table_ok && e->it_ok && e->d_it_scratch && s.d_escaped;
-    std::vector<uint8_t> grp((size_t)n, 0);
+    std::vector<int> &rest = e->scratch_rest;
+    std::vector<uint8_t> &rgrp = e->scratch_grp;
+    rest.clear(); rgrp.clear();
     int cnt[3] = {0, 0, 0}, nf[3] = {0, 0, 0};
+    int pos_it = 0;
     for (int t = 0; t < n; t++) {
         const gact_tile_desc &d = descs[t];
         if (d.ref_set >= GACT_MAX_SETS || d.query_set >= GACT_MAX_SETS || d.ref_len < 0 || d.query_len < 0 ||
@@ -418,39 +425,37 @@ int check_descs(gact_engine *e, int n, const gact_tile_desc *descs, Slot &s)
             return fail(e, GACT_ERR_ARG, "tile descriptor " + std::to_string(t) + " out of range");
         int g = (table_ok && !e->sets[d.query_set].range_has_exc(d.query_off, d.query_len)) ? 1 : 2;
         if (g == 1 && it_on && !d.first && d.ref_len == T && d.query_len == T && e->sets[d.ref_set].h_exc.empty()) g = 0;
-        grp[(size_t)t] = (uint8_t)g;
         cnt[g]++;
         if (d.first) nf[g]++;
         cells += (unsigned long long)d.ref_len * (unsigned long long)d.query_len;
+        if (g == 0) s.h_order[pos_it++] = t;
+        else { rest.push_back(t); rgrp.push_back((uint8_t)g); }
     }
     // the inter-task kernel takes whole warps of 64 tiles and only batches that fill the GPU; the rest joins group 1
     int n_it = (cnt[0] / 64) * 64;
     if (n_it < e->it_min_tiles) n_it = 0;
-    {
-        int spill = cnt[0] - n_it;
-        for (int t = n - 1; t >= 0 && spill > 0; t--)
-            if (grp[(size_t)t] == 0) { grp[(size_t)t] = 1; spill--; }
-        cnt[1] += cnt[0] - n_it;
-        cnt[0] = n_it;
-    }
+    for (int k = n_it; k < cnt[0]; k++) { rest.push_back(s.h_order[k]); rgrp.push_back(1); }
+    cnt[1] += cnt[0] - n_it;
+    cnt[0] = n_it;
     s.n_it = n_it;
     s.n_lut = cnt[0] + cnt[1];
     s.n_first_lut = nf[1];
     s.n_first = nf[1] + nf[2];
     s.cells = cells;
     int fpos[3] = {0, 0, nf[1]};
-    for (int t = 0; t < n; t++) if (descs[t].first) s.h_first[fpos[grp[(size_t)t]]++] = t;
-    // h_order: [inter-task tiles, in input order][score-table tiles][raw-byte tiles]; the wavefront groups are counting-
-    // sorted by reference length, longest first: the two tiles a warp aligns side by side then have the same number of
-    // wavefront steps, and the long tiles start first
+    for (size_t k = 0; k < rest.size(); k++) if (descs[rest[k]].first) s.h_first[fpos[rgrp[k]]++] = rest[k];
+    // h_order: [inter-task tiles][score-table tiles][raw-byte tiles]; the wavefront groups are counting-sorted by reference
+    // length, longest first: the two tiles a warp aligns side by side then have the same number of wavefront steps, and
+    // the long tiles start first
     std::vector<int> start(2 * ((size_t)T + 2) + 1, 0);
-    auto bucket = [&](int t) { return (size_t)(grp[(size_t)t] - 1) * ((size_t)T + 1) + (size_t)(T - descs[t].ref_len); };
-    int pos_it = 0;
-    for (int t = 0; t < n; t++) { if (grp[(size_t)t] == 0) s.h_order[pos_it++] = t; else start[bucket(t) + 1]++; }
+    auto bucket = [&](size_t k) { return (size_t)(rgrp[k] - 1) * ((size_t)T + 1) + (size_t)(T - descs[rest[k]].ref_len); };
+    for (size_t k = 0; k < rest.size(); k++) start[bucket(k) + 1]++;
     for (size_t k = 1; k < start.size(); k++) start[k] += start[k - 1];
-    for (int t = 0; t < n; t++) if (grp[(size_t)t] != 0) s.h_order[n_it + start[bucket(t)]++] = t;
+    for (size_t k = 0; k < rest.size(); k++) s.h_order[n_it + start[bucket(k)]++] = rest[k];
     return GACT_OK;
 }
+
+void par_memcpy(void *dst, const void *src, size_t bytes);
 
 int enqueue(gact_engine *e, Slot &s, int n, const gact_tile_desc *descs)
 {
@@ -459,7 +464,7 @@ int enqueue(gact_engine *e, Slot &s, int n, const gact_tile_desc *descs)
     if (rc) return rc;
     s.n = n;
     if (n == 0) return GACT_OK;
-    memcpy(s.h_descs, descs, (size_t)n * sizeof(gact_tile_desc));
+    par_memcpy(s.h_descs, descs, (size_t)n * sizeof(gact_tile_desc));
     // upload on the H2D copy stream; the compute stream waits for it, so the copy of batch k+1
     // overlaps the kernels of batch k
     CU(e, cudaMemcpyAsync(s.d_descs, s.h_descs, (size_t)n * sizeof(gact_tile_desc), cudaMemcpyHostToDevice, e->s_h2d));
@@ -487,6 +492,22 @@ int download(gact_engine *e, Slot &s, bool want_states)
     return GACT_OK;
 }
 
+// copy-out of a large batch on a few threads (one core moves ~8 GB/s; 1 Mi tiles are 134 MB of results + states)
+void par_memcpy(void *dst, const void *src, size_t bytes)
+{
+    const size_t MIN = (size_t)4 << 20;
+    if (bytes < 2 * MIN) { memcpy(dst, src, bytes); return; }
+    const int parts = (int)std::min<size_t>(4, bytes / MIN);
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / parts) + 63) & ~(size_t)63;
+    for (int p = 1; p < parts; p++) {
+        const size_t a = per * p, b = (p == parts - 1) ? bytes : std::min(bytes, per * (p + 1));
+        if (a < b) th.emplace_back([=] { memcpy((char *)dst + a, (const char *)src + a, b - a); });
+    }
+    memcpy(dst, src, std::min(bytes, per));
+    for (auto &t : th) t.join();
+}
+
 int finish(gact_engine *e, Slot &s, gact_tile_result *results, uint32_t *packed_states, bool states_copied)
 {
     CU(e, cudaEventSynchronize(s.ev_done));
@@ -497,8 +518,8 @@ int finish(gact_engine *e, Slot &s, gact_tile_result *results, uint32_t *packed_
         e->stats.kernel_ms += ms;
         e->last_n_it = s.n_it;
         e->last_n_escaped = s.n_it > 0 ? s.h_it_info[1] : 0;
-        if (results) memcpy(results, s.h_results, (size_t)s.n * sizeof(gact_tile_result));
-        if (packed_states && states_copied) memcpy(packed_states, s.h_states, (size_t)s.n * e->pitch_words * 4);
+        if (results) par_memcpy(results, s.h_results, (size_t)s.n * sizeof(gact_tile_result));
+        if (packed_states && states_copied) par_memcpy(packed_states, s.h_states, (size_t)s.n * e->pitch_words * 4);
     }
     e->stats.tiles += s.n;
     e->stats.cells += s.cells;

@@ -1,5 +1,5 @@
 """Summarise an .ncu-rep (one kernel launch, --set full) into a small text file for profiles/.
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/name.txt [profiles/name.json tiles_in_launch "capture note"]
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/name.txt [profiles/name.json tiles_in_launch "capture note" [cells_in_launch]]
 The optional JSON carries the raw counters bench.py turns into pipe-utilisation figures (roofline.executed)."""
 import csv
 import json
@@ -46,6 +46,8 @@ if len(sys.argv) > 4:
     JW = WANT + ["sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_lsu.sum",
                  "sm__inst_executed.sum", "smsp__cycles_active.avg", "sm__cycles_active.avg", "gpc__cycles_elapsed.max"]
     rec = {"tiles": int(sys.argv[4]), "capture": sys.argv[5] if len(sys.argv) > 5 else rep, "unit_of": {}}
+    if len(sys.argv) > 6:
+        rec["cells"] = int(sys.argv[6])
     for h, u, v in zip(hdr, units, val):
         if h in JW:
             try:
