@@ -101,6 +101,7 @@ struct gact_engine {
     S16HPlan s16h_lat;        // chain kernel, one tile per warp: used when candidates < chain slots (latency bound)
     // inter-task tile kernel (gact_kernels_it.cuh): one lane per pair of full, non-first tiles
     bool it_ok = false;       // usable for these parameters
+    bool it_qs = false;       // query columns staged in shared memory too
     ITGeom it_geom{};
     int it_ctas = 0, it_min_tiles = 0;
     uint8_t *d_it_scratch = nullptr;      // GACT_MAX_INFLIGHT regions: strip edges, row score tables, code words per resident warp
@@ -309,8 +310,12 @@ int plan_launch(gact_engine *e)
         if (const char *m = getenv("GACT_IT_MIN")) e->it_min_tiles = std::max(64, atoi(m));
         e->it_edge_b = it_edge_bytes(T); e->it_win_b = it_win_bytes(e->it_geom);
         e->it_region_bytes = (size_t)e->it_ctas * 4 * (e->it_edge_b + e->it_win_b);
-        e->it_smem = 4 * it_smem_per_warp(T);
-        e->it_ok = cudaFuncSetAttribute((const void *)gact_tile_it_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        // the query columns join the reference rows in shared memory where that still leaves room for every CTA of an SM
+        e->it_qs = (4 * it_smem_per_warp(T, true) + 1024) * (size_t)it_per_sm <= (size_t)227 * 1024;
+        if (const char *q = getenv("GACT_IT_QS")) e->it_qs = atoi(q) != 0;
+        e->it_smem = 4 * it_smem_per_warp(T, e->it_qs);
+        const void *fn = e->it_qs ? (const void *)gact_tile_it_kernel<true> : (const void *)gact_tile_it_kernel<false>;
+        e->it_ok = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)e->it_smem) == cudaSuccess;      // scratch is allocated with the batch slots
         if (!e->it_ok) cudaGetLastError();
     }
@@ -348,9 +353,9 @@ int launch_batch(gact_engine *e, Slot &s, cudaStream_t st, int scratch_region)
             uint32_t *win = reinterpret_cast<uint32_t *>(base + warps * e->it_edge_b);
             CU(e, cudaEventRecord(s.ev_it0, st));
             CU(e, cudaStreamWaitEvent(s.st_it, s.ev_it0, 0));
-            gact_tile_it_kernel<<<grid, 128, e->it_smem, s.st_it>>>(kp, e->it_geom, s.d_descs, s.d_order, n_batches, s.d_results,
-                                                                    s.d_states, e->pitch_words, s.d_counters + 4, s.d_escaped, edge, win,
-                                                                    e->it_win_b / 4);
+            auto kern = e->it_qs ? gact_tile_it_kernel<true> : gact_tile_it_kernel<false>;
+            kern<<<grid, 128, e->it_smem, s.st_it>>>(kp, e->it_geom, s.d_descs, s.d_order, n_batches, s.d_results, s.d_states,
+                                                     e->pitch_words, s.d_counters + 4, s.d_escaped, edge, win, e->it_win_b / 4);
             CU(e, cudaEventRecord(s.ev_it1, s.st_it));
             e->stats.kernel_launches++;
         }

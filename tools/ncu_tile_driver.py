@@ -10,7 +10,10 @@ import pygact as G
 import synth
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 17
-mb = synth.tile_microbatch(n, tile_size=320, seed=42)
+kw = {}
+if "FULL_FRAC" in os.environ:      # e.g. FULL_FRAC=1 FIRST_FRAC=0: only tiles the inter-task kernel takes
+    kw = dict(full_frac=float(os.environ["FULL_FRAC"]), first_frac=float(os.environ.get("FIRST_FRAC", "0.055")))
+mb = synth.tile_microbatch(n, tile_size=320, seed=42, **kw)
 with G.GactEngine(max_tiles=n) as eng:
     eng.upload(G.SET_REF, [mb["ref"].tobytes()])
     eng.upload(G.SET_READS, [mb["query"].tobytes()])
@@ -22,5 +25,8 @@ with G.GactEngine(max_tiles=n) as eng:
     for _ in range(3):
         eng.run_staged()
     eng.sync()
-    print("kernel_ms", eng.last_kernel_ms(), "tiles", n)
-    eng.fetch_staged()
+    ms = eng.last_kernel_ms()
+    res, _ = eng.fetch_staged()
+    info = eng.tile_path_info() if hasattr(eng, "tile_path_info") else None
+    cells = int((d["ref_len"].astype(np.int64) * d["query_len"]).sum())
+    print("kernel_ms", ms, "tiles", n, "gcups", cells / ms / 1e6, "path", info, "checksum", int(res["score"].astype(np.int64).sum()))
