@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 #include <thread>
+#include <chrono>
 #include <new>
 
 #include "gact_common.cuh"
@@ -20,6 +21,7 @@
 #include "gact_kernels_it.cuh"
 #include "dsoft.cuh"
 #include "seed_build.cuh"
+#include "host_pool.h"
 #include <algorithm>
 
 using namespace gact;
@@ -78,6 +80,17 @@ struct Slot {
 struct gact_chain_state;
 static void destroy_chain_state(struct gact_engine *e);
 
+// One thread's share of check_descs: tiles [a, b) validated and routed.
+struct alignas(128) CheckPart {
+    std::vector<int> it, rest;
+    std::vector<uint8_t> grp;
+    int cnt[3], nf[3], bad;
+    unsigned long long cells;
+};
+
+static HostPool &host_pool() { static HostPool *p = new HostPool; return *p; }   // lives as long as the process
+static int g_copy_threads = 4;
+
 struct gact_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -103,7 +116,8 @@ struct gact_engine {
     bool it_ok = false;       // usable for these parameters
     bool it_qs = false;       // query columns staged in shared memory too
     ITGeom it_geom{};
-    int it_ctas = 0, it_min_tiles = 0;
+    int it_ctas = 0, it_min_tiles = 0;     // it_ctas: resident groups of 4 warps
+    int it_cta_warps = 1;                  // warps per CTA of the launch (1, 2 or 4; GACT_IT_CTA_WARPS)
     uint8_t *d_it_scratch = nullptr;      // GACT_MAX_INFLIGHT regions: strip edges, row score tables, code words per resident warp
     size_t it_region_bytes = 0, it_edge_b = 0, it_win_b = 0, it_smem = 0;
     SeqSetHost sets[GACT_MAX_SETS];
@@ -112,10 +126,15 @@ struct gact_engine {
     bool staged = false;
     bool slots_ready = false;
     double last_kernel_ms = -1.0;
+    // GACT_HOST_TRACE=1: host-side milliseconds of the tile path, printed when the engine is destroyed
+    bool host_trace = false;
+    double ht_check = 0, ht_copy_in = 0, ht_launch = 0, ht_sync = 0, ht_copy_out = 0;
     int last_n_it = 0, last_n_escaped = 0;   // inter-task kernel: tiles it took / handed back in the last finished batch
     struct gact_chain_state *chains = nullptr;       // gact_engine_extend_* state (created on first use)
     std::vector<int> scratch_rest;                   // check_descs work arrays (kept to avoid reallocation per batch)
     std::vector<uint8_t> scratch_grp;
+    std::vector<CheckPart> check_parts;
+    int host_threads = 4;                            // threads of the host-side passes over a large batch (GACT_HOST_THREADS)
     gact_stats stats{};
     std::string err;
 };
@@ -298,6 +317,14 @@ int plan_launch(gact_engine *e)
     // inter-task kernel: full, non-first tiles, one lane per pair of tiles (experiment knobs: GACT_IT=0 switches it off,
     // GACT_IT_BAND=<half-width of the tagged band>, GACT_IT_MIN=<fewest eligible tiles of a batch worth a launch>)
     e->it_ok = false;
+    if (const char *h = getenv("GACT_HOST_TRACE")) e->host_trace = atoi(h) != 0;
+    {
+        // host-side passes over a large batch (descriptor check + routing, copy-in, copy-out): half of the cores, 2..8
+        const int hw = (int)std::thread::hardware_concurrency();
+        e->host_threads = std::max(2, std::min(8, hw / 2));
+        if (const char *h = getenv("GACT_HOST_THREADS")) e->host_threads = std::max(1, std::min(16, atoi(h)));
+        g_copy_threads = e->host_threads;
+    }
     const char *itv = getenv("GACT_IT");
     if (e->s16h.ok && e->s16h.lut_ok && T % IT_CS == 0 && T / IT_CS <= IT_MAX_STRIPS && T >= 64 && !(itv && atoi(itv) == 0)) {
         int W = std::max(32, (et + 7) / 8);         // a 15 % error channel drifts ~0.045 et off the diagonal, +- 0.37 sqrt(et)
@@ -310,6 +337,7 @@ int plan_launch(gact_engine *e)
         if (const char *m = getenv("GACT_IT_MIN")) e->it_min_tiles = std::max(64, atoi(m));
         e->it_edge_b = it_edge_bytes(T); e->it_win_b = it_win_bytes(e->it_geom);
         e->it_region_bytes = (size_t)e->it_ctas * 4 * (e->it_edge_b + e->it_win_b);
+        if (const char *w = getenv("GACT_IT_CTA_WARPS")) { const int v = atoi(w); if (v == 1 || v == 2 || v == 4) e->it_cta_warps = v; }
         // the query columns join the reference rows in shared memory where that still leaves room for every CTA of an SM
         e->it_qs = (4 * it_smem_per_warp(T, true) + 1024) * (size_t)it_per_sm <= (size_t)227 * 1024;
         if (const char *q = getenv("GACT_IT_QS")) e->it_qs = atoi(q) != 0;
@@ -345,8 +373,12 @@ int launch_batch(gact_engine *e, Slot &s, cudaStream_t st, int scratch_region)
             kp.s16_bias = e->s16h.bias;
             kp.one = 1;
             const int n_batches = s.n_it / 64;
-            int grid = (n_batches + 3) / 4;
-            if (grid > e->it_ctas) grid = e->it_ctas;
+            // one-warp CTAs: a warp that finds no further group of 64 tiles retires at once and hands its registers to
+            // the kernels queued behind (the next batch's, the wavefront kernels), instead of idling until the slowest
+            // warp of a 4-warp CTA is done
+            const int cw = e->it_cta_warps;
+            int grid = (n_batches + cw - 1) / cw;
+            if (grid > e->it_ctas * 4 / cw) grid = e->it_ctas * 4 / cw;
             uint8_t *base = e->d_it_scratch + (size_t)scratch_region * e->it_region_bytes;
             const size_t warps = (size_t)e->it_ctas * 4;
             uint2 *edge = reinterpret_cast<uint2 *>(base);
@@ -354,7 +386,7 @@ int launch_batch(gact_engine *e, Slot &s, cudaStream_t st, int scratch_region)
             CU(e, cudaEventRecord(s.ev_it0, st));
             CU(e, cudaStreamWaitEvent(s.st_it, s.ev_it0, 0));
             auto kern = e->it_qs ? gact_tile_it_kernel<true> : gact_tile_it_kernel<false>;
-            kern<<<grid, 128, e->it_smem, s.st_it>>>(kp, e->it_geom, s.d_descs, s.d_order, n_batches, s.d_results, s.d_states,
+            kern<<<grid, 32 * cw, e->it_smem / 4 * cw, s.st_it>>>(kp, e->it_geom, s.d_descs, s.d_order, n_batches, s.d_results, s.d_states,
                                                      e->pitch_words, s.d_counters + 4, s.d_escaped, edge, win, e->it_win_b / 4);
             CU(e, cudaEventRecord(s.ev_it1, s.st_it));
             e->stats.kernel_launches++;
@@ -411,30 +443,63 @@ int launch_batch(gact_engine *e, Slot &s, cudaStream_t st, int scratch_region)
 int check_descs(gact_engine *e, int n, const gact_tile_desc *descs, Slot &s)
 {
     const int T = e->params.tile_size;
-    unsigned long long cells = 0;
     const bool table_ok = use_s16(e) && e->s16h.lut_ok;
     // group 0: inter-task kernel (full, non-first tiles of the score-table group), 1: score-table wavefront kernels,
-    // 2: raw-byte wavefront kernels.  One pass: inter-task tiles go straight into h_order (their order does not matter),
-    // the others are collected and counting-sorted afterwards (they are the minority of a large batch).
+    // 2: raw-byte wavefront kernels.  One pass over the descriptors, on a few threads for a large batch (10 ns per tile
+    // on one core is 10 ms per Mi tiles, as long as the kernels of a 256 Ki batch take): inter-task tiles go straight
+    // into h_order (their order does not matter), the others are collected and counting-sorted afterwards (they are
+    // the minority of a large batch).
     const bool it_on = table_ok && e->it_ok && e->d_it_scratch && s.d_escaped;
+    const int parts = n >= (1 << 16) ? std::max(1, std::min(8, e->host_threads)) : 1;
+    if ((int)e->check_parts.size() < parts) e->check_parts.resize((size_t)parts);
+    auto work = [&](int p) {
+        // everything a tile touches is local to the thread (the parts sit next to each other in memory)
+        CheckPart c;
+        {
+            CheckPart &mine = e->check_parts[(size_t)p];
+            c.it.swap(mine.it); c.rest.swap(mine.rest); c.grp.swap(mine.grp);     // keep the capacity of the last batch
+        }
+        c.it.clear(); c.rest.clear(); c.grp.clear();
+        for (int g = 0; g < 3; g++) c.cnt[g] = c.nf[g] = 0;
+        c.cells = 0; c.bad = -1;
+        const int a = (int)((long long)n * p / parts), b = (int)((long long)n * (p + 1) / parts);
+        for (int t = a; t < b && c.bad < 0; t++) {
+            const gact_tile_desc &d = descs[t];
+            if (d.ref_set >= GACT_MAX_SETS || d.query_set >= GACT_MAX_SETS || d.ref_len < 0 || d.query_len < 0 ||
+                d.ref_len > T || d.query_len > T || d.ref_off < 0 || d.query_off < 0 ||
+                d.ref_off + d.ref_len > e->sets[d.ref_set].len || d.query_off + d.query_len > e->sets[d.query_set].len) {
+                c.bad = t;
+                break;
+            }
+            int g = (table_ok && !e->sets[d.query_set].range_has_exc(d.query_off, d.query_len)) ? 1 : 2;
+            if (g == 1 && it_on && !d.first && d.ref_len == T && d.query_len == T && e->sets[d.ref_set].h_exc.empty()) g = 0;
+            c.cnt[g]++;
+            if (d.first) c.nf[g]++;
+            c.cells += (unsigned long long)d.ref_len * (unsigned long long)d.query_len;
+            if (g == 0) c.it.push_back(t);
+            else { c.rest.push_back(t); c.grp.push_back((uint8_t)g); }
+        }
+        CheckPart &mine = e->check_parts[(size_t)p];
+        mine.it.swap(c.it); mine.rest.swap(c.rest); mine.grp.swap(c.grp);
+        for (int g = 0; g < 3; g++) { mine.cnt[g] = c.cnt[g]; mine.nf[g] = c.nf[g]; }
+        mine.cells = c.cells; mine.bad = c.bad;
+    };
+    host_pool().run(parts, work);
     std::vector<int> &rest = e->scratch_rest;
     std::vector<uint8_t> &rgrp = e->scratch_grp;
     rest.clear(); rgrp.clear();
+    unsigned long long cells = 0;
     int cnt[3] = {0, 0, 0}, nf[3] = {0, 0, 0};
     int pos_it = 0;
-    for (int t = 0; t < n; t++) {
-        const gact_tile_desc &d = descs[t];
-        if (d.ref_set >= GACT_MAX_SETS || d.query_set >= GACT_MAX_SETS || d.ref_len < 0 || d.query_len < 0 ||
-            d.ref_len > T || d.query_len > T || d.ref_off < 0 || d.query_off < 0 ||
-            d.ref_off + d.ref_len > e->sets[d.ref_set].len || d.query_off + d.query_len > e->sets[d.query_set].len)
-            return fail(e, GACT_ERR_ARG, "tile descriptor " + std::to_string(t) + " out of range");
-        int g = (table_ok && !e->sets[d.query_set].range_has_exc(d.query_off, d.query_len)) ? 1 : 2;
-        if (g == 1 && it_on && !d.first && d.ref_len == T && d.query_len == T && e->sets[d.ref_set].h_exc.empty()) g = 0;
-        cnt[g]++;
-        if (d.first) nf[g]++;
-        cells += (unsigned long long)d.ref_len * (unsigned long long)d.query_len;
-        if (g == 0) s.h_order[pos_it++] = t;
-        else { rest.push_back(t); rgrp.push_back((uint8_t)g); }
+    for (int p = 0; p < parts; p++) {
+        const CheckPart &c = e->check_parts[(size_t)p];
+        if (c.bad >= 0) return fail(e, GACT_ERR_ARG, "tile descriptor " + std::to_string(c.bad) + " out of range");
+        for (int g = 0; g < 3; g++) { cnt[g] += c.cnt[g]; nf[g] += c.nf[g]; }
+        cells += c.cells;
+        if (!c.it.empty()) memcpy(s.h_order + pos_it, c.it.data(), c.it.size() * sizeof(int));
+        pos_it += (int)c.it.size();
+        rest.insert(rest.end(), c.rest.begin(), c.rest.end());
+        rgrp.insert(rgrp.end(), c.grp.begin(), c.grp.end());
     }
     // the inter-task kernel takes whole warps of 64 tiles and only batches that fill the GPU; the rest joins group 1
     int n_it = (cnt[0] / 64) * 64;
@@ -461,15 +526,22 @@ int check_descs(gact_engine *e, int n, const gact_tile_desc *descs, Slot &s)
 }
 
 void par_memcpy(void *dst, const void *src, size_t bytes);
+static double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 int enqueue(gact_engine *e, Slot &s, int n, const gact_tile_desc *descs)
 {
     if (n < 0 || n > e->max_tiles || (n > 0 && !descs)) return fail(e, GACT_ERR_ARG, "bad tile count");
+    const double t0 = e->host_trace ? now_ms() : 0;
     int rc = check_descs(e, n, descs, s);
     if (rc) return rc;
     s.n = n;
     if (n == 0) return GACT_OK;
+    const double t1 = e->host_trace ? now_ms() : 0;
     par_memcpy(s.h_descs, descs, (size_t)n * sizeof(gact_tile_desc));
+    if (e->host_trace) { e->ht_check += t1 - t0; e->ht_copy_in += now_ms() - t1; }
     // upload on the H2D copy stream; the compute stream waits for it, so the copy of batch k+1
     // overlaps the kernels of batch k
     CU(e, cudaMemcpyAsync(s.d_descs, s.h_descs, (size_t)n * sizeof(gact_tile_desc), cudaMemcpyHostToDevice, e->s_h2d));
@@ -500,22 +572,22 @@ int download(gact_engine *e, Slot &s, bool want_states)
 // copy-out of a large batch on a few threads (one core moves ~8 GB/s; 1 Mi tiles are 134 MB of results + states)
 void par_memcpy(void *dst, const void *src, size_t bytes)
 {
-    const size_t MIN = (size_t)4 << 20;
+    const size_t MIN = (size_t)2 << 20;
     if (bytes < 2 * MIN) { memcpy(dst, src, bytes); return; }
-    const int parts = (int)std::min<size_t>(4, bytes / MIN);
-    std::vector<std::thread> th;
+    const int parts = (int)std::min<size_t>((size_t)g_copy_threads, bytes / MIN);
     const size_t per = ((bytes / parts) + 63) & ~(size_t)63;
-    for (int p = 1; p < parts; p++) {
+    host_pool().run(parts, [=](int p) {
         const size_t a = per * p, b = (p == parts - 1) ? bytes : std::min(bytes, per * (p + 1));
-        if (a < b) th.emplace_back([=] { memcpy((char *)dst + a, (const char *)src + a, b - a); });
-    }
-    memcpy(dst, src, std::min(bytes, per));
-    for (auto &t : th) t.join();
+        if (a < b) memcpy((char *)dst + a, (const char *)src + a, b - a);
+    });
 }
 
 int finish(gact_engine *e, Slot &s, gact_tile_result *results, uint32_t *packed_states, bool states_copied)
 {
+    const double t0 = e->host_trace ? now_ms() : 0;
     CU(e, cudaEventSynchronize(s.ev_done));
+    const double t1 = e->host_trace ? now_ms() : 0;
+    if (e->host_trace) e->ht_sync += t1 - t0;
     if (s.n > 0) {
         float ms = 0.f;
         CU(e, cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
@@ -525,6 +597,7 @@ int finish(gact_engine *e, Slot &s, gact_tile_result *results, uint32_t *packed_
         e->last_n_escaped = s.n_it > 0 ? s.h_it_info[1] : 0;
         if (results) par_memcpy(results, s.h_results, (size_t)s.n * sizeof(gact_tile_result));
         if (packed_states && states_copied) par_memcpy(packed_states, s.h_states, (size_t)s.n * e->pitch_words * 4);
+        if (e->host_trace) e->ht_copy_out += now_ms() - t1;
     }
     e->stats.tiles += s.n;
     e->stats.cells += s.cells;
@@ -676,6 +749,10 @@ bad:
 void gact_engine_destroy(gact_engine *e)
 {
     if (!e) return;
+    if (e->host_trace)
+        fprintf(stderr, "GACT_HOST_TRACE tile path, host ms: check_descs %.1f  copy-in %.1f  launch+enqueue %.1f  wait(sync) %.1f  copy-out %.1f  "
+                "(%llu batches, %llu tiles)\n", e->ht_check, e->ht_copy_in, e->ht_launch, e->ht_sync, e->ht_copy_out,
+                (unsigned long long)e->stats.batches, (unsigned long long)e->stats.tiles);
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (int k = 0; k < GACT_MAX_INFLIGHT; k++) if (e->cs[k]) cudaStreamSynchronize(e->cs[k]);
@@ -836,6 +913,7 @@ int gact_engine_submit(gact_engine *e, int n, const gact_tile_desc *descs)
     CU(e, cudaStreamWaitEvent(st, s.ev_fork, 0));
     int rc = enqueue(e, s, n, descs);
     if (rc) return rc;
+    const double tl = e->host_trace ? now_ms() : 0;
     if (n > 0) {
         rc = launch_batch(e, s, st, overlap ? e->head : 0);
         if (rc) return rc;
@@ -843,6 +921,7 @@ int gact_engine_submit(gact_engine *e, int n, const gact_tile_desc *descs)
         if (rc) return rc;
     }
     CU(e, cudaEventRecord(s.ev_done, n > 0 ? e->s_d2h : st));
+    if (e->host_trace) e->ht_launch += now_ms() - tl;
     s.busy = true;
     e->head = (e->head + 1) % GACT_MAX_INFLIGHT;
     e->inflight++;
