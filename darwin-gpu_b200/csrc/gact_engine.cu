@@ -64,6 +64,7 @@ struct Slot {
     int *d_counters = nullptr;            // [0] first pass, [1] main pass, [2] / [3] the same for the raw-byte group
     int n_lut = 0, n_first_lut = 0;       // tiles / first tiles whose query window has no exception: they come first in
                                           // h_order / h_first and run on the score-table kernels, the rest on raw bytes
+    int n_narrow = 0;                     // trailing part of the n_lut tiles that runs on the narrow mapping (s16h_narrow)
     int n_it = 0;                         // leading part of the n_lut tiles that goes to the inter-task kernel (multiple of 64)
     int *d_escaped = nullptr;             // tiles the inter-task kernel handed back (band left): redone by the wavefront kernel
     int *h_it_info = nullptr;             // pinned: [0] batches claimed, [1] tiles handed back, of this slot's last launch
@@ -84,7 +85,7 @@ static void destroy_chain_state(struct gact_engine *e);
 struct alignas(128) CheckPart {
     std::vector<int> it, rest;
     std::vector<uint8_t> grp;
-    int cnt[3], nf[3], bad;
+    int cnt[4], nf[4], bad;
     unsigned long long cells;
 };
 
@@ -111,6 +112,7 @@ struct gact_engine {
     size_t smem_main = 0;
     uint8_t *d_gscratch = nullptr;
     S16HPlan s16h;            // packed s16x2 kernels: two tiles per warp (tile_size <= 320) or one (<= 1024); ok = usable for these params
+    S16HPlan s16h_narrow;     // tile kernel, strips of half the width: tiles whose query window is at most half a tile wide
     S16HPlan s16h_lat;        // chain kernel, one tile per warp: used when candidates < chain slots (latency bound)
     // inter-task tile kernel (gact_kernels_it.cuh): one lane per pair of full, non-first tiles
     bool it_ok = false;       // usable for these parameters
@@ -314,6 +316,11 @@ int plan_launch(gact_engine *e)
     if (s16h_make_plan(e->params, e->num_sms, wps, &e->s16h) != 0 ||
         s16h_make_plan(e->params, e->num_sms, wps, &e->s16h_lat, true) != 0)
         return fail(e, GACT_ERR_CUDA, "s16h kernel attribute setup failed");
+    // narrow mapping for tiles with a query window of at most half a tile (GACT_NARROW=0 switches it off)
+    e->s16h_narrow = S16HPlan();
+    if (e->s16h.ok && !(getenv("GACT_NARROW") && atoi(getenv("GACT_NARROW")) == 0) &&
+        s16h_make_plan(e->params, e->num_sms, wps, &e->s16h_narrow, false, true) != 0)
+        return fail(e, GACT_ERR_CUDA, "s16h kernel attribute setup failed");
     // inter-task kernel: full, non-first tiles, one lane per pair of tiles (experiment knobs: GACT_IT=0 switches it off,
     // GACT_IT_BAND=<half-width of the tagged band>, GACT_IT_MIN=<fewest eligible tiles of a batch worth a launch>)
     e->it_ok = false;
@@ -399,9 +406,14 @@ int launch_batch(gact_engine *e, Slot &s, cudaStream_t st, int scratch_region)
             s16h_launch_first(e->s16h, e->kp, s.d_descs, s.d_first + s.n_first_lut, nf_byte, s.d_eff, s.d_counters + 2, st, false);
             e->stats.kernel_launches++;
         }
-        if (s.n_lut - s.n_it > 0) {
-            s16h_launch(e->s16h, e->kp, s.d_descs, s.d_order + s.n_it, s.n_lut - s.n_it, s.d_eff, s.d_results, s.d_states,
-                        e->pitch_words, s.d_counters + 1, st, scratch_region, true);
+        if (s.n_lut - s.n_it - s.n_narrow > 0) {
+            s16h_launch(e->s16h, e->kp, s.d_descs, s.d_order + s.n_it, s.n_lut - s.n_it - s.n_narrow, s.d_eff, s.d_results,
+                        s.d_states, e->pitch_words, s.d_counters + 1, st, scratch_region, true);
+            e->stats.kernel_launches++;
+        }
+        if (s.n_narrow > 0) {
+            s16h_launch(e->s16h_narrow, e->kp, s.d_descs, s.d_order + s.n_lut - s.n_narrow, s.n_narrow, s.d_eff, s.d_results,
+                        s.d_states, e->pitch_words, s.d_counters + 7, st, scratch_region, true);
             e->stats.kernel_launches++;
         }
         if (n_byte > 0) {
@@ -445,11 +457,13 @@ int check_descs(gact_engine *e, int n, const gact_tile_desc *descs, Slot &s)
     const int T = e->params.tile_size;
     const bool table_ok = use_s16(e) && e->s16h.lut_ok;
     // group 0: inter-task kernel (full, non-first tiles of the score-table group), 1: score-table wavefront kernels,
-    // 2: raw-byte wavefront kernels.  One pass over the descriptors, on a few threads for a large batch (10 ns per tile
+    // 2: raw-byte wavefront kernels, 3: score-table wavefront kernel in its narrow mapping (non-first tiles whose query
+    // window fits strips of half the width: the same rows at half the work per wavefront step).  One pass over the descriptors, on a few threads for a large batch (10 ns per tile
     // on one core is 10 ms per Mi tiles, as long as the kernels of a 256 Ki batch take): inter-task tiles go straight
     // into h_order (their order does not matter), the others are collected and counting-sorted afterwards (they are
     // the minority of a large batch).
     const bool it_on = table_ok && e->it_ok && e->d_it_scratch && s.d_escaped;
+    const int narrow_cols = (table_ok && e->s16h_narrow.ok) ? e->s16h_narrow.cols() : 0;
     const int parts = n >= (1 << 16) ? std::max(1, std::min(8, e->host_threads)) : 1;
     if ((int)e->check_parts.size() < parts) e->check_parts.resize((size_t)parts);
     auto work = [&](int p) {
@@ -460,7 +474,7 @@ int check_descs(gact_engine *e, int n, const gact_tile_desc *descs, Slot &s)
             c.it.swap(mine.it); c.rest.swap(mine.rest); c.grp.swap(mine.grp);     // keep the capacity of the last batch
         }
         c.it.clear(); c.rest.clear(); c.grp.clear();
-        for (int g = 0; g < 3; g++) c.cnt[g] = c.nf[g] = 0;
+        for (int g = 0; g < 4; g++) c.cnt[g] = c.nf[g] = 0;
         c.cells = 0; c.bad = -1;
         const int a = (int)((long long)n * p / parts), b = (int)((long long)n * (p + 1) / parts);
         for (int t = a; t < b && c.bad < 0; t++) {
@@ -473,6 +487,7 @@ int check_descs(gact_engine *e, int n, const gact_tile_desc *descs, Slot &s)
             }
             int g = (table_ok && !e->sets[d.query_set].range_has_exc(d.query_off, d.query_len)) ? 1 : 2;
             if (g == 1 && it_on && !d.first && d.ref_len == T && d.query_len == T && e->sets[d.ref_set].h_exc.empty()) g = 0;
+            else if (g == 1 && narrow_cols > 0 && !d.first && d.query_len <= narrow_cols) g = 3;
             c.cnt[g]++;
             if (d.first) c.nf[g]++;
             c.cells += (unsigned long long)d.ref_len * (unsigned long long)d.query_len;
@@ -481,7 +496,7 @@ int check_descs(gact_engine *e, int n, const gact_tile_desc *descs, Slot &s)
         }
         CheckPart &mine = e->check_parts[(size_t)p];
         mine.it.swap(c.it); mine.rest.swap(c.rest); mine.grp.swap(c.grp);
-        for (int g = 0; g < 3; g++) { mine.cnt[g] = c.cnt[g]; mine.nf[g] = c.nf[g]; }
+        for (int g = 0; g < 4; g++) { mine.cnt[g] = c.cnt[g]; mine.nf[g] = c.nf[g]; }
         mine.cells = c.cells; mine.bad = c.bad;
     };
     host_pool().run(parts, work);
@@ -489,12 +504,12 @@ int check_descs(gact_engine *e, int n, const gact_tile_desc *descs, Slot &s)
     std::vector<uint8_t> &rgrp = e->scratch_grp;
     rest.clear(); rgrp.clear();
     unsigned long long cells = 0;
-    int cnt[3] = {0, 0, 0}, nf[3] = {0, 0, 0};
+    int cnt[4] = {0, 0, 0, 0}, nf[4] = {0, 0, 0, 0};
     int pos_it = 0;
     for (int p = 0; p < parts; p++) {
         const CheckPart &c = e->check_parts[(size_t)p];
         if (c.bad >= 0) return fail(e, GACT_ERR_ARG, "tile descriptor " + std::to_string(c.bad) + " out of range");
-        for (int g = 0; g < 3; g++) { cnt[g] += c.cnt[g]; nf[g] += c.nf[g]; }
+        for (int g = 0; g < 4; g++) { cnt[g] += c.cnt[g]; nf[g] += c.nf[g]; }
         cells += c.cells;
         if (!c.it.empty()) memcpy(s.h_order + pos_it, c.it.data(), c.it.size() * sizeof(int));
         pos_it += (int)c.it.size();
@@ -507,18 +522,25 @@ int check_descs(gact_engine *e, int n, const gact_tile_desc *descs, Slot &s)
     for (int k = n_it; k < cnt[0]; k++) { rest.push_back(s.h_order[k]); rgrp.push_back(1); }
     cnt[1] += cnt[0] - n_it;
     cnt[0] = n_it;
+    if (cnt[3] > 0 && cnt[3] < 64) {                 // not worth a launch of its own
+        for (auto &g : rgrp) if (g == 3) g = 1;
+        cnt[1] += cnt[3];
+        cnt[3] = 0;
+    }
     s.n_it = n_it;
-    s.n_lut = cnt[0] + cnt[1];
+    s.n_lut = cnt[0] + cnt[1] + cnt[3];
+    s.n_narrow = cnt[3];
     s.n_first_lut = nf[1];
     s.n_first = nf[1] + nf[2];
     s.cells = cells;
-    int fpos[3] = {0, 0, nf[1]};
+    int fpos[4] = {0, 0, nf[1], 0};
     for (size_t k = 0; k < rest.size(); k++) if (descs[rest[k]].first) s.h_first[fpos[rgrp[k]]++] = rest[k];
-    // h_order: [inter-task tiles][score-table tiles][raw-byte tiles]; the wavefront groups are counting-sorted by reference
-    // length, longest first: the two tiles a warp aligns side by side then have the same number of wavefront steps, and
-    // the long tiles start first
-    std::vector<int> start(2 * ((size_t)T + 2) + 1, 0);
-    auto bucket = [&](size_t k) { return (size_t)(rgrp[k] - 1) * ((size_t)T + 1) + (size_t)(T - descs[rest[k]].ref_len); };
+    // h_order: [inter-task tiles][score-table tiles][narrow score-table tiles][raw-byte tiles]; the wavefront groups are
+    // counting-sorted by reference length, longest first: the two tiles a warp aligns side by side then have the same
+    // number of wavefront steps, and the long tiles start first
+    static const int slot_of_group[4] = {0, 0, 2, 1};
+    std::vector<int> start(3 * ((size_t)T + 2) + 1, 0);
+    auto bucket = [&](size_t k) { return (size_t)slot_of_group[rgrp[k]] * ((size_t)T + 1) + (size_t)(T - descs[rest[k]].ref_len); };
     for (size_t k = 0; k < rest.size(); k++) start[bucket(k) + 1]++;
     for (size_t k = 1; k < start.size(); k++) start[k] += start[k - 1];
     for (size_t k = 0; k < rest.size(); k++) s.h_order[n_it + start[bucket(k)]++] = rest[k];
@@ -763,6 +785,7 @@ void gact_engine_destroy(gact_engine *e)
     if (e->d_it_scratch) cudaFree(e->d_it_scratch);
     s16h_free_plan(&e->s16h);
     s16h_free_plan(&e->s16h_lat);
+    s16h_free_plan(&e->s16h_narrow);
     destroy_chain_state(e);
     if (e->s_h2d) { cudaStreamSynchronize(e->s_h2d); cudaStreamDestroy(e->s_h2d); }
     if (e->s_d2h) { cudaStreamSynchronize(e->s_d2h); cudaStreamDestroy(e->s_d2h); }

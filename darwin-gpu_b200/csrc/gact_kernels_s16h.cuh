@@ -92,21 +92,30 @@ struct DirWinH {
 // <= 0: lanes that have not reached row 1 yet run pseudo rows against the sentinel, which reproduce the border values,
 // so the wavefront loop needs no per-lane "am I active" branch) and PAD words of slack on the right (rows past the
 // end of a tile: their results are never used, the words only have to be readable).
+// Column capacity of a mapping is TS = CS * 2 * LANES; its ROW capacity TR is the same except for the narrow mappings
+// (16 lanes, strips of 4 / 5 columns), which exist for the tiles of a batch whose query window is at most half a tile
+// wide: they take reference windows of the full tile size (TR = 2 TS) at half the work per wavefront step.
+__host__ __device__ constexpr int s16h_row_cap(int CS, int LANES)
+{
+    return (LANES == 16 && CS <= 5) ? 4 * CS * LANES : 2 * CS * LANES;
+}
 __host__ __device__ constexpr size_t s16h_seq_bytes(int CS, int LANES)
 {
-    const int TS = CS * 2 * LANES, PAD = 2 * LANES;
-    return (size_t)((((PAD + TS + 2 + PAD) * 4 + (TS + 2) * 4) + 15) & ~15) + (size_t)(((2 * (TS / 16 + 2) + (TS / 32 + 2)) * 4 + 15) & ~15);
+    const int TS = CS * 2 * LANES, TR = s16h_row_cap(CS, LANES), PAD = 2 * LANES;
+    return (size_t)((((PAD + TR + 2 + PAD) * 4 + (TS + 2 + TR + 2) * 2) + 15) & ~15) +
+           (size_t)((((TR / 16 + 2) + (TS / 16 + 2) + (TR / 32 + 2)) * 4 + 15) & ~15);
 }
 
 template <int CS, int LANES>
 struct SegCtx {
-    static constexpr int TS = CS * 2 * LANES;
+    static constexpr int TS = CS * 2 * LANES;              // columns
+    static constexpr int TR = s16h_row_cap(CS, LANES);     // rows
     static constexpr int PAD = 2 * LANES;
     int lane, seg, sl, segbase;
     uint32_t *rr;            // rr[i]: substitution table of R[i] (LUT) or enc(R[i]) | enc(R[i-1]) << 16
     uint16_t *qs, *rb;       // enc(Q[j]), enc(R[i])
-    uint32_t *wr, *wq;       // the tile's 2-bit packed words as loaded from HBM (reference / query), <= TS/16 + 2 each
-    uint32_t *we;            // exception bitmap words of the reference window (<= TS/32 + 2), sets with exceptions only
+    uint32_t *wr, *wq;       // the tile's 2-bit packed words as loaded from HBM (reference <= TR/16 + 2, query <= TS/16 + 2)
+    uint32_t *we;            // exception bitmap words of the reference window (<= TR/32 + 2), sets with exceptions only
     void *dirbase;
     // constants of the biased x16 domain
     int B, KO, KI, KD, ONE, et, match, mismatch, gap_open, gap_extend;
@@ -123,10 +132,10 @@ struct SegCtx {
         constexpr int TPW = 32 / LANES;
         uint8_t *my = smem + ((size_t)warp * TPW + seg) * seq_stride;
         rr = reinterpret_cast<uint32_t *>(my) + PAD;
-        qs = reinterpret_cast<uint16_t *>(my + (PAD + TS + 2 + PAD) * 4);
+        qs = reinterpret_cast<uint16_t *>(my + (PAD + TR + 2 + PAD) * 4);
         rb = qs + (TS + 2);
-        wr = reinterpret_cast<uint32_t *>(my + ((((PAD + TS + 2 + PAD) * 4 + (TS + 2) * 4) + 15) & ~15));
-        wq = wr + (TS / 16 + 2);
+        wr = reinterpret_cast<uint32_t *>(my + ((((PAD + TR + 2 + PAD) * 4 + (TS + 2 + TR + 2) * 2) + 15) & ~15));
+        wq = wr + (TR / 16 + 2);
         we = wq + (TS / 16 + 2);
         // direction window: per-segment global scratch, or (SMEMWIN) the shared memory behind this segment's sequence arrays
         if (SMEMWIN) dirbase = (void *)(my + s16h_seq_bytes(CS, LANES));
@@ -145,7 +154,7 @@ struct SegCtx {
         // sentinel rows <= 0 (written once: staging only writes rows >= 1) and defined slack on the right
         const uint32_t sent = lut ? lut_mis : (SENT_R | (SENT_R << 16));
         for (int x = sl; x <= PAD; x += LANES) rr[-x] = sent;
-        for (int x = 1 + sl; x < TS + 2 + PAD; x += LANES) rr[x] = sent;
+        for (int x = 1 + sl; x < TR + 2 + PAD; x += LANES) rr[x] = sent;
         __syncwarp();
     }
 };
@@ -340,7 +349,7 @@ __device__ __forceinline__ int seg_dp(const SegCtx<CS, LANES> &cx, const uint32_
         if (sl == 0) recv = cx.borderD_raw;
         const uint32_t inG = __byte_perm(recv, eG, 0x5410);
         const uint32_t inD = __byte_perm(recv, eD, 0x5432);
-        GACT_CHK(2, k - 2 * sl >= -cx.PAD && k + 1 - 2 * sl < cx.TS + 2 + cx.PAD);
+        GACT_CHK(2, k - 2 * sl >= -cx.PAD && k + 1 - 2 * sl < cx.TR + 2 + cx.PAD);
         const uint32_t rlo = GACT_RR_PREFETCH ? rnext : rrp[k], rhi = rprev;
         if (GACT_RR_PREFETCH) rnext = rrp[k + 1];
         uint32_t hd = diag, dv = inD;
@@ -383,7 +392,7 @@ __device__ __forceinline__ int seg_dp(const SegCtx<CS, LANES> &cx, const uint32_
         if (sl == 0) recv = cx.borderD_tag;
         const uint32_t inG = __byte_perm(recv, eG, 0x5410);
         const uint32_t inD = __byte_perm(recv, eD, 0x5432);
-        GACT_CHK(2, k - 2 * sl >= -cx.PAD && k + 1 - 2 * sl < cx.TS + 2 + cx.PAD);
+        GACT_CHK(2, k - 2 * sl >= -cx.PAD && k + 1 - 2 * sl < cx.TR + 2 + cx.PAD);
         const uint32_t rlo = GACT_RR_PREFETCH ? rnext : rrp[k], rhi = rprev;
         if (GACT_RR_PREFETCH) rnext = rrp[k + 1];
         uint32_t hd = diag, dv = inD;
@@ -480,7 +489,7 @@ __device__ __forceinline__ SegTrace seg_traceback(const SegCtx<CS, LANES> &cx, c
         const int it = i - sl, jt = j - sl;
         const bool inb = inM && it >= i0 && jt >= j0;
         const int code_t = inb ? dw.load(it, jt) : 0;
-        GACT_CHK(3, !inb || (it >= 1 && it <= cx.TS + 1 && jt >= 1 && jt <= cx.TS + 1));
+        GACT_CHK(3, !inb || (it >= 1 && it <= cx.TR + 1 && jt >= 1 && jt <= cx.TS + 1));
         const bool match_t = inb && (cx.rb[it] == cx.qs[jt]);
         const unsigned mm = (__ballot_sync(FULL, match_t) >> cx.segbase) & SEGMASK;
         unsigned run;
@@ -949,6 +958,7 @@ struct S16HPlan {
     uint8_t *d_scratch = nullptr;        // GACT_MAX_INFLIGHT regions of scratch_bytes: kernels of consecutive batches may overlap
     size_t scratch_bytes = 0;
     int tpw() const { return 32 / lanes; }
+    int cols() const { return CS * 2 * lanes; }                      // widest query window of a tile
     int slots() const { return ctas * warps_per_cta * tpw(); }       // tiles / chains resident at once
 };
 
@@ -969,6 +979,9 @@ typedef void (*s16h_chain_fn)(const KParams, const ChainCall *, int, ChainResult
 
 inline s16h_fn s16h_pick(int CS, int lanes, bool lut)
 {
+    // narrow mappings: score-table tile kernel only
+    if (lanes == 16 && CS == 5) return lut ? gact_tile_s16h_kernel<5, 16, true> : nullptr;
+    if (lanes == 16 && CS == 4) return lut ? gact_tile_s16h_kernel<4, 16, true> : nullptr;
     s16h_fn f = nullptr;
 #define S16H_X(C, L) f = lut ? gact_tile_s16h_kernel<C, L, true> : gact_tile_s16h_kernel<C, L, false>
     S16H_DISPATCH(CS, lanes, S16H_X);
@@ -1014,7 +1027,10 @@ inline void s16h_free_plan(S16HPlan *pl)
 // latency = true: plan for the chain kernel only, tile_size <= 320: one tile per warp (32 lanes, strips of 4 / 5
 // columns) with the direction window in shared memory and two CTAs (8 warps) per SM at most: used when a shard has
 // few candidates, so that the longest read's serial tile chain finishes sooner.
-inline int s16h_make_plan(const gact_params &p, int num_sms, int warps_per_sm, S16HPlan *pl, bool latency = false)
+// narrow = true: plan for the tile kernel only, tile_size <= 320: the two-tiles-per-warp mapping with strips of half
+// the width (4 / 5 columns) for tiles whose query window is at most narrow_cols() wide.
+inline int s16h_make_plan(const gact_params &p, int num_sms, int warps_per_sm, S16HPlan *pl, bool latency = false,
+                          bool narrow = false)
 {
     s16h_free_plan(pl);
     *pl = S16HPlan();
@@ -1032,6 +1048,10 @@ inline int s16h_make_plan(const gact_params &p, int num_sms, int warps_per_sm, S
         if (T > 320 || !pl->lut_ok) return 0;        // larger tiles already run one per warp; their window does not fit
         CS = (T <= 256) ? 4 : 5; lanes = 32;
         pl->smem_window = true;
+    }
+    if (narrow) {
+        if (T > 320 || T < 64 || !pl->lut_ok) return 0;
+        CS = (T <= 256) ? 4 : 5; lanes = 16;
     }
     pl->CS = CS; pl->lanes = lanes;
     pl->win_rows = (et + 1 < T) ? et + 1 : T;
@@ -1053,6 +1073,13 @@ inline int s16h_make_plan(const gact_params &p, int num_sms, int warps_per_sm, S
         pl->smem = (size_t)pl->warps_per_cta * pl->tpw() * pl->seq_bytes;
         pl->scratch_bytes = (size_t)pl->ctas * pl->warps_per_cta * pl->tpw() * pl->dir_bytes;
         if (cudaMalloc(&pl->d_scratch, GACT_MAX_INFLIGHT * pl->scratch_bytes) != cudaSuccess) { cudaGetLastError(); pl->d_scratch = nullptr; return 0; }
+    }
+    if (narrow) {
+        if (cudaFuncSetAttribute((const void *)s16h_pick(CS, lanes, true), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)pl->smem) != cudaSuccess)
+            return -1;
+        pl->ok = true;
+        return 0;
     }
     for (int lut = 0; lut < 2 && !latency; lut++)
         if (cudaFuncSetAttribute((const void *)s16h_pick(CS, lanes, lut != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,

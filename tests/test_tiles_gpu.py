@@ -221,6 +221,41 @@ def test_inter_task_kernel_matches_oracle(pygact, oracle, monkeypatch, band, til
     assert len(bad) == 0, f"{len(bad)} of {n} tiles differ, first {bad[:5]}: gpu {res[bad[:3]]} cpu {ores[bad[:3]]}"
 
 
+@pytest.mark.parametrize("tile,overlap,scores", [(320, 120, (1, -1, -1, -1)), (256, 96, (2, -3, -5, -2)), (320, 0, (1, -1, -2, -1)),
+                                                 (300, 100, (1, -1, -1, -1)), (64, 10, (1, -3, 0, 0)), (200, 190, (1, -2, -3, -1))])
+def test_narrow_mapping_matches_oracle(pygact, oracle, monkeypatch, tile, overlap, scores):
+    """Ragged batch (every window length uniform in 1..tile_size): non-first tiles whose query window fits strips of half the
+    width run on the narrow mapping of the wavefront kernel (reference windows up to the full tile size), the others on the
+    regular one.  Every tile must equal the oracle, and the results must not depend on the mapping (GACT_NARROW=0)."""
+    G, O = pygact, oracle
+    import synth
+    n = 3000
+    mb = synth.tile_microbatch(n, tile_size=tile, seed=3 * tile + overlap, full_frac=0.1, first_frac=0.1)
+    # some tiles at the corners of the narrow mapping's range: widest query it takes, with the longest reference
+    cols = (4 if tile <= 256 else 5) * 32
+    k = np.flatnonzero(mb["first"] == 0)[:40]
+    mb["query_len"][k[:20]] = min(cols, tile)
+    mb["ref_len"][k[:20]] = tile
+    mb["query_len"][k[20:]] = min(cols + 1, tile)              # one column too wide: regular mapping
+    mb["ref_off"] = np.clip(mb["ref_off"], 0, len(mb["ref"]) - tile - 1)
+    ref = mb["ref"]
+    out = []
+    for narrow in ("1", "0"):
+        monkeypatch.setenv("GACT_NARROW", narrow)
+        with G.GactEngine(*scores, tile_size=tile, tile_overlap=overlap, max_tiles=n) as eng:
+            eng.upload(G.SET_REF, [ref.tobytes()])
+            eng.upload(G.SET_READS, [mb["query"].tobytes()])
+            out.append(eng.align_tiles(engine_descs(G, mb)) + (eng.stats()["kernel_launches"],))
+    assert out[0][2] == out[1][2] + 1                               # the narrow group had its own launch
+    assert (out[0][0] == out[1][0]).all()
+    from helpers import unpack_all                                  # state words beyond n_states are not defined
+    P = out[0][1].shape[1] * 16
+    assert (unpack_all(out[0][1], out[0][0]["n_states"], P) == unpack_all(out[1][1], out[1][0]["n_states"], P)).all()
+    ores, ost = O.align_batch(ref, mb["query"], oracle_descs(O, mb), scores=scores, et=tile - overlap, max_len=tile, n_threads=8)
+    bad = compare_batch(out[0][0], out[0][1], ores, ost)
+    assert len(bad) == 0, f"{len(bad)} of {n} tiles differ, first {bad[:5]}: gpu {out[0][0][bad[:3]]} cpu {ores[bad[:3]]}"
+
+
 def test_async_submit_wait_matches_sync(pygact):
     G = pygact
     import synth
