@@ -48,7 +48,8 @@ ALU_OPS_PER_CELL_FLOOR = 2.5
 # this round's ncu captures of the two kernels of a tile step: the inter-task kernel (full, non-first tiles) and the
 # wavefront kernel (everything else)
 NCU_SUMMARIES = [("inter_task", os.path.join(ROOT, "profiles", "r2_inter_task_kernel_ncu.json")),
-                 ("wavefront", os.path.join(ROOT, "profiles", "r2_wavefront_kernel_ncu.json"))]
+                 ("wavefront", os.path.join(ROOT, "profiles", "r2_wavefront_kernel_ncu.json")),
+                 ("wavefront_narrow", os.path.join(ROOT, "profiles", "r2_narrow_kernel_ncu.json"))]
 TILE, OVERLAP = 320, 120
 SCORES = (1, -1, -1, -1)
 
@@ -594,7 +595,11 @@ def main():
                     pass
             n_it = path_info["inter_task"]
             cells_it = n_it * TILE * TILE
-            share = {"inter_task": cells_it, "wavefront": cells - cells_it}
+            # the engine's routing rule (check_descs): non-first, not full, query window of at most 160 columns -> narrow mapping
+            rl64, ql64 = mb["ref_len"].astype(np.int64), mb["query_len"].astype(np.int64)
+            is_narrow = (mb["first"] == 0) & (ql64 <= 160) & ~((rl64 == TILE) & (ql64 == TILE))
+            cells_narrow = int((rl64 * ql64)[is_narrow].sum()) if os.environ.get("GACT_NARROW", "1") != "0" and "wavefront_narrow" in caps else 0
+            share = {"inter_task": cells_it, "wavefront": cells - cells_it - cells_narrow, "wavefront_narrow": cells_narrow}
             if all(k in caps and caps[k].get("cells") for k, v in share.items() if v > 0):
                 smsp = 4 * 148
                 inst = sum(caps[k]["smsp__inst_executed.sum"] / caps[k]["cells"] * v for k, v in share.items() if v > 0)
@@ -613,10 +618,11 @@ def main():
                          "issue_slot_frac": inst / (kernel_ms * 1e-3 * smsp * sm_clock_hz),
                          "alu_pipe_frac": alu / (kernel_ms * 1e-3 * smsp * sm_clock_hz * 0.5),
                          "sm_clock_mhz_used": sm_clock_hz / 1e6,
-                         "note": "the two kernels overlap on two streams; fractions are over the whole step"}
+                         "note": "the inter-task kernel overlaps the wavefront kernels on two streams; fractions are over the whole step"}
         roof = {"bound": "int_issue",
                 "kernel": ("tile step = gact_tile_it_kernel (%d of %d tiles: full, non-first) overlapped with gact_first_s16h / "
-                           "gact_tile_s16h_kernel<10,16,true> (the rest), packed s16x2 DPX" % (path_info["inter_task"], n)) if packed
+                           "gact_tile_s16h_kernel<10,16,true> / <5,16,true> (the rest; the narrow mapping for query windows of at "
+                           "most 160 columns), packed s16x2 DPX" % (path_info["inter_task"], n)) if packed
                 else "gact_tile_i32 kernel",
                 "achieved": achieved, "peak": peak_alu,
                 "unit": "G ALU-pipe lane-ops/s: achieved = cells/s x %.1f (algorithmic floor of the %s recurrence, 5 ALU-pipe "

@@ -7,6 +7,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 python tools/ncu_tile_driver.py 524288 > gpurun_out/ncu_plain_tile.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:gact_tile_it_kernel -s 1 -c 1 -o gpurun_out/r2_it -f python tools/ncu_tile_driver.py 524288 > gpurun_out/ncu_it.log 2>&1
 python tools/ncu_tile_driver.py 524288 > gpurun_out/ncu_plain_tile2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:gact_tile_s16h_kernel -s 2 -c 1 -o gpurun_out/r2_wavefront -f python tools/ncu_tile_driver.py 524288 > gpurun_out/ncu_wavefront.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:.*gact_tile_s16h_kernel<\(int\)10.*' -s 2 -c 1 -o gpurun_out/r2_wavefront -f python tools/ncu_tile_driver.py 524288 > gpurun_out/ncu_wavefront.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:.*gact_tile_s16h_kernel<\(int\)5.*' -s 1 -c 1 -o gpurun_out/r2_narrow -f python tools/ncu_tile_driver.py 524288 > gpurun_out/ncu_narrow.log 2>&1
 ls -la gpurun_out/*.ncu-rep
 echo done
