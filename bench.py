@@ -95,7 +95,8 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []          # (arrival time, line)
+        self.t_begin = None      # start of the timed region: earlier samples (warm-up) are not used
 
     def start(self):
         try:
@@ -108,7 +109,12 @@ class ClockSampler:
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def begin(self):
+        """The timed region starts now.  nvidia-smi was started before the warm-up (it needs a few hundred ms to come up,
+        as long as a short timed region lasts), so samples exist from the first 100 ms of the region on."""
+        self.t_begin = time.time()
 
     def stop(self):
         if not self.proc:
@@ -120,7 +126,13 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t_end = time.time()
+        inside = [ln for t, ln in self.lines if self.t_begin is None or self.t_begin <= t <= t_end]
+        if not inside and self.lines:
+            # a timed region shorter than one sampling period: the sample closest to it (the GPU runs the same kernels in the
+            # warm-up just before)
+            inside = [min(self.lines, key=lambda x: abs(x[0] - (self.t_begin or t_end)))[1]]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -497,12 +509,13 @@ def main():
 
     # ---- leg 1: device-resident (value) --------------------------------------------------
     eng.stage(d)
+    sampler = ClockSampler(local)
+    sampler.start()                    # nvidia-smi comes up during the warm-up; only samples after begin() are used
     for _ in range(args.warmup):
         eng.run_staged()
     eng.sync()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.begin()
     launches0 = eng.stats()["kernel_launches"]
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     with torch.cuda.stream(stream):

@@ -1,0 +1,10 @@
+#!/bin/bash
+run() { env "$@" 2>/dev/null | python -c "
+import json,sys
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('value %.0f  e2e %.0f  e2e ms %.2f' % (d['value'], d['e2e']['value'], d['e2e']['ms_per_step']))
+"; }
+B="python bench.py --steps 5 --warmup 3 --no-reads-leg --no-cpu-baseline"
+for c in 50 72 86 100; do echo "== carveout $c"; run GACT_CARVEOUT=$c $B; done
+echo "== carveout 64 narrow off"; run GACT_CARVEOUT=64 GACT_NARROW=0 $B
