@@ -362,7 +362,9 @@ int plan_launch(gact_engine *e)
         // different carve-outs cannot share an SM: the wavefront kernels of a batch and the inter-task kernel of the next
         // then take turns instead of filling each other's tails.  Measured on 7-batch e2e steps: 34.2 ms without, 30.6 ms
         // with 72 % (164 KB); the device-resident step is unchanged.  GACT_CARVEOUT=<percent> overrides, -1 leaves the default.
-        int pct = 72;
+        // Only up to tile_size 320, where it was measured: larger tiles need more shared memory per inter-task warp than
+        // 164 KB holds at full occupancy.
+        int pct = T <= 320 ? 72 : -1;
         if (const char *c = getenv("GACT_CARVEOUT")) pct = atoi(c);
         if (pct >= 0 && pct <= 100) {
             for (int lut = 0; lut < 2; lut++) {
