@@ -111,6 +111,11 @@ struct SegCtx {
     static constexpr int TS = CS * 2 * LANES;              // columns
     static constexpr int TR = s16h_row_cap(CS, LANES);     // rows
     static constexpr int PAD = 2 * LANES;
+    // layout of a segment's carve-out (init): rr | qs, rb | wr, wq, we -- it must fit what the host reserves
+    static constexpr size_t OFF_WORDS = (size_t)((((PAD + TR + 2 + PAD) * 4 + (TS + 2 + TR + 2) * 2) + 15) & ~15);
+    static constexpr size_t OFF_END = OFF_WORDS + (size_t)((TR / 16 + 2) + (TS / 16 + 2) + (TR / 32 + 2)) * 4;
+    static_assert(OFF_END <= s16h_seq_bytes(CS, LANES), "segment arrays exceed s16h_seq_bytes");
+    static_assert((PAD + TR + 2 + PAD) * 4 % 2 == 0 && OFF_WORDS % 16 == 0, "alignment of the 16- and 32-bit arrays");
     int lane, seg, sl, segbase;
     uint32_t *rr;            // rr[i]: substitution table of R[i] (LUT) or enc(R[i]) | enc(R[i-1]) << 16
     uint16_t *qs, *rb;       // enc(Q[j]), enc(R[i])
@@ -134,7 +139,7 @@ struct SegCtx {
         rr = reinterpret_cast<uint32_t *>(my) + PAD;
         qs = reinterpret_cast<uint16_t *>(my + (PAD + TR + 2 + PAD) * 4);
         rb = qs + (TS + 2);
-        wr = reinterpret_cast<uint32_t *>(my + ((((PAD + TR + 2 + PAD) * 4 + (TS + 2 + TR + 2) * 2) + 15) & ~15));
+        wr = reinterpret_cast<uint32_t *>(my + OFF_WORDS);
         wq = wr + (TR / 16 + 2);
         we = wq + (TS / 16 + 2);
         // direction window: per-segment global scratch, or (SMEMWIN) the shared memory behind this segment's sequence arrays
